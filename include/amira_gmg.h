@@ -1,0 +1,143 @@
+/* amira_gmg.h -- C ABI of the B200-native GeneMerGraph build (libamira_gmg.so).
+ *
+ * The upstream project (Danderson123/Amira) is pure Python and has no FFI; the boundary this
+ * library slots in behind is the Python class boundary
+ *     GeneMerGraph(readDict, kmerSize, gene_positions=None)        amira/construct_graph.py:31-102
+ *     GeneMerGraph.filter_graph(minNodeCoverage, minEdgeCoverage)   amira/construct_graph.py:523-540
+ *     GeneMerGraph.remove_low_coverage_components(c)                amira/construct_graph.py:950-958
+ * reached through build_graph / build_multiprocessed_graph           amira/graph_utils.py:12-14, 105-124.
+ * Each entry point below names the upstream code it replaces.  INTEGRATION.md shows the ctypes stub
+ * a maintainer adds on the upstream side.
+ *
+ * Conventions: every function returns an int status (AMIRA_OK == 0); amira_last_error() returns a
+ * thread-local message for the last failure.  No exception crosses the ABI.  The caller owns every
+ * input and output buffer; the library owns only the opaque handle and its device memory.  One
+ * handle per (host thread, device); a handle is not thread-safe, distinct handles may be used
+ * concurrently.  All device work of a handle is stream-ordered on the handle's stream.
+ *
+ * Gene ids: int32, id = strand * rank, strand in {+1,-1}, rank in 1..V = position of the gene name
+ * in the vocabulary sorted by int(sha256(pickle.dumps(name))) ascending, so that the signed integer
+ * order equals the order of upstream's signed gene hashes (amira/construct_gene.py:91-93) and the
+ * canonical orientation of every gene-mer is the one upstream picks (construct_gene_mer.py:15-39).
+ */
+#ifndef AMIRA_GMG_H
+#define AMIRA_GMG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amira_gmg amira_gmg;
+
+enum {
+    AMIRA_OK = 0,
+    AMIRA_E_BLANK_GENE = 1,    /* "Gene information is missing"          construct_gene.py:52 */
+    AMIRA_E_BAD_STRAND = 2,    /* "Strand information missing for: ..."  construct_gene.py:58 */
+    AMIRA_E_EMPTY_NAME = 3,    /* "Gene name information missing ..."    construct_gene.py:62 */
+    AMIRA_E_UNKNOWN_GENE = 4,  /* token not in the supplied vocabulary */
+    AMIRA_E_PALINDROME = 5,    /* "Gene-mer and reverse complement gene-mer are identical"  construct_gene_mer.py:23 */
+    AMIRA_E_EMPTY_GENEMER = 6, /* k == 0 with a non-empty read: "Gene-mer is empty"         construct_gene_mer.py:47 */
+    AMIRA_E_MULTI_EDGE = 7,    /* remove_node on a node with two edges to one neighbour: upstream TypeError */
+    AMIRA_E_ARG = 8,
+    AMIRA_E_STATE = 9,         /* call order violated (e.g. export before build) */
+    AMIRA_E_CUDA = 10,
+    AMIRA_E_NOMEM = 11,
+    AMIRA_E_NCCL = 12
+};
+
+/* phases timed with CUDA events on the handle's stream (amira_gmg_phase_ms) */
+enum {
+    AMIRA_PH_H2D = 0,        /* host -> device copy of the CSR input */
+    AMIRA_PH_WINDOWS = 1,    /* per-read window counts + scan */
+    AMIRA_PH_INSERT = 2,     /* k_insert_windows: enumerate, canonicalise, hash, node + edge tables */
+    AMIRA_PH_ORDER = 3,      /* first-seen ordering of nodes and edges, node/edge arrays */
+    AMIRA_PH_REMAP = 4,      /* per-window slot -> node index */
+    AMIRA_PH_INCIDENCE = 5,  /* node -> reads CSR */
+    AMIRA_PH_ADJACENCY = 6,  /* node -> forward/backward edge CSR */
+    AMIRA_PH_COMPONENTS = 7, /* connected components */
+    AMIRA_PH_FILTER = 8,     /* last filter / component removal */
+    AMIRA_PH_EXCHANGE = 9,   /* multi-GPU all-to-all + merge */
+    AMIRA_PH_COUNT = 10
+};
+
+const char *amira_last_error(void);
+const char *amira_version(void);
+
+/* Gene-call token parsing: "+name" / "-name" -> signed id.  Replaces Gene.__init__ /
+ * split_gene_and_strand (construct_gene.py:48-67) and convert_genes (construct_read.py:5-8).
+ * Tokens are concatenated UTF-8 with tok_off[n_tok+1] byte offsets; vocabulary names likewise, in
+ * SHA-rank order (names already have spaces replaced by '_').  Spaces in a token's name are mapped
+ * to '_' before the lookup.  On error returns the code above and writes the index of the offending
+ * token to *bad_token (if non-NULL). */
+int amira_vocab_encode(const char *tokens_utf8, const int64_t *tok_off, int64_t n_tok,
+                       const char *vocab_utf8, const int64_t *vocab_off, int32_t n_vocab,
+                       int32_t *out_signed_ids, int64_t *bad_token);
+
+int amira_gmg_create(amira_gmg **h, int device, void *cuda_stream /* NULL: library-owned stream */);
+void amira_gmg_destroy(amira_gmg *h);
+
+/* optional capacity hints (expected unique nodes / undirected edges); 0 = automatic */
+int amira_gmg_reserve(amira_gmg *h, int64_t n_nodes_hint, int64_t n_edges_hint);
+int amira_gmg_set_profiling(amira_gmg *h, int enabled);
+int amira_gmg_phase_ms(const amira_gmg *h, int phase, float *ms);
+int amira_gmg_kernel_launches(const amira_gmg *h, int64_t *n);
+
+/* The build: GeneMerGraph.__init__ (construct_graph.py:45-102) for R reads in CSR form.
+ * signed_ids[read_off[R]], read_off[R+1]; pos_start/pos_end (nullable) are per-call read
+ * coordinates (gene_positions, construct_read.py:46-52).  input_on_device != 0: the pointers are
+ * device pointers valid on the handle's stream (they are borrowed until the next build/destroy).
+ * Asynchronous with respect to the host unless a capacity retry is needed; errors detected on the
+ * device (AMIRA_E_PALINDROME) are reported by amira_gmg_sync / amira_gmg_sizes / the exports. */
+int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read_off, int64_t R, int32_t k,
+                    const int32_t *pos_start, const int32_t *pos_end, int input_on_device);
+
+/* wait for the handle's stream; returns the deferred status of the last build / filter */
+int amira_gmg_sync(amira_gmg *h);
+
+/* sizes of the current (possibly filtered) graph */
+int amira_gmg_sizes(amira_gmg *h, int64_t *n_nodes, int64_t *n_edges, int64_t *n_windows,
+                    int64_t *n_incidence, int64_t *n_fw, int64_t *n_bw, int64_t *n_short);
+
+/* Nodes in upstream `_nodes` insertion order (construct_graph.py:196-212):
+ * key[n_nodes*k] canonical signed ids, cov (Node.nodeCoverage), first_dir (direction of the
+ * first-seen GeneMer), component (assign_component_ids, :920-927), reads CSR (Node.listOfReads as
+ * read indices, ascending), forward / backward edge-index CSR (Node.forwardEdgeHashes /
+ * backwardEdgeHashes, construct_node.py:79-101).  Any output pointer may be NULL to skip it. */
+int amira_gmg_export_nodes(amira_gmg *h, int32_t *key, uint32_t *cov, int8_t *first_dir, uint32_t *component,
+                           int64_t *reads_off, int32_t *reads, int64_t *fw_off, int32_t *fw_edges,
+                           int64_t *bw_off, int32_t *bw_edges);
+
+/* Edges in upstream `_edges` insertion order (construct_graph.py:268-277): source / target node
+ * index, stored (first-seen) directions, coverage. */
+int amira_gmg_export_edges(amira_gmg *h, int32_t *src, int32_t *tgt, int8_t *sd, int8_t *td, uint32_t *cov);
+
+/* Per-read lists (_readNodes / _readNodeDirections / _readNodePositions, construct_graph.py:165-178):
+ * win_off[R+1], node_idx[W] (-1 = None after filtering), dir[W] (0 where None), start/end[W]
+ * (only if positions were supplied; -1 where None), is_short[R] (_shortReads), to_correct[R]
+ * (_readsToCorrect). */
+int amira_gmg_export_reads(amira_gmg *h, int64_t *win_off, int32_t *node_idx, int8_t *dir, int32_t *start,
+                           int32_t *end, uint8_t *is_short, uint8_t *to_correct);
+
+/* remove_low_coverage_components (construct_graph.py:950-958) and filter_graph (:523-540) */
+int amira_gmg_remove_low_coverage_components(amira_gmg *h, uint32_t min_component_cov);
+int amira_gmg_filter(amira_gmg *h, uint32_t min_node_cov, uint32_t min_edge_cov);
+
+/* Multi-GPU (one process per GPU): reads are sharded contiguously over ranks, canonical gene-mers
+ * are owned by hash range, partial tables are routed with an NCCL all-to-all.  nccl_unique_id is
+ * the 128-byte ncclUniqueId of rank 0.  After comm_init, amira_gmg_build takes this rank's shard and
+ * first_read_global (amira_gmg_set_shard) and every rank ends with the global node / edge tables. */
+int amira_gmg_nccl_unique_id(void *out_128_bytes);
+int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int world);
+int amira_gmg_set_shard(amira_gmg *h, int64_t first_read_global, int64_t first_call_global);
+
+/* Micro-benchmark for the atomic roofline: random-address 32-bit RED.ADD and 64-bit
+ * CAS into a table of table_bytes; returns operations per second of each. */
+int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, double *red_add_per_s,
+                          double *cas_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMIRA_GMG_H */
