@@ -1,0 +1,115 @@
+// common.cuh -- error plumbing, device buffers, hashing and table slot layouts shared by the
+// GeneMerGraph kernels.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/amira_gmg.h"
+
+namespace amira {
+
+void set_error(const char *fmt, ...);
+
+#define AMIRA_CUDA(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            amira::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,              \
+                             cudaGetErrorString(_e));                                          \
+            return _e == cudaErrorMemoryAllocation ? AMIRA_E_NOMEM : AMIRA_E_CUDA;             \
+        }                                                                                      \
+    } while (0)
+
+#define AMIRA_TRY(expr)                \
+    do {                               \
+        int _s = (expr);               \
+        if (_s != AMIRA_OK) return _s; \
+    } while (0)
+
+// grow-only device allocation, reused across builds (Amira rebuilds the graph ~10-100x per sample)
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return AMIRA_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return AMIRA_E_NOMEM;
+        }
+        cap = want;
+        return AMIRA_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// ---- table layouts -----------------------------------------------------------------------------
+// Node table slot (16 B, two per 32 B sector).  `word` packs, from the top: a 22-bit fingerprint
+// of the canonical gene-mer, the 41-bit global call index p of the FIRST window seen with this
+// gene-mer, and one bit that is set when that first window was the reverse complement of the
+// canonical form.  Because the fingerprint is a function of the key, atomicMin over words of one
+// key is atomicMin over p: the slot always names the first occurrence in (read, window) order,
+// which is upstream's dict insertion order, and carries that occurrence's direction.
+// The key itself is not stored: it is ids[p .. p+k) (reverse-complemented when the bit is set).
+// `cov` counts from 0xFFFFFFFF so that the whole table is initialised by one memset(0xFF).
+struct NodeSlot {
+    unsigned long long word;
+    unsigned int cov;  // occurrences - 1
+    unsigned int aux;  // node index once the first-seen order is known
+};
+static_assert(sizeof(NodeSlot) == 16, "NodeSlot must be 16 bytes");
+
+constexpr unsigned long long EMPTY64 = ~0ull;
+constexpr int P_BITS = 41;
+constexpr unsigned long long P_MASK = (1ull << P_BITS) - 1;
+constexpr int FP_SHIFT = P_BITS + 1;
+constexpr unsigned int FP_MAX = (1u << (64 - FP_SHIFT)) - 2;  // all-ones is reserved for EMPTY
+
+// Edge table slot (32 B = one sector).  One entry per UNDIRECTED adjacency {lo, hi, rel}: lo <= hi
+// are node-table slot numbers, rel = sd*td.  Upstream creates two directed Edge objects per
+// adjacent window pair (forward S->T and reverse T->S, construct_graph.py:246-262) whose identity
+// is (source, target, sd*td) (construct_edge.py:104-124); both are always created by the same pair
+// event and always have equal coverage, so one entry suffices: `ord` = (p << 2 | source_is_hi << 1
+// | sd < 0) of the first pair event (atomicMin), from which both directed edges, their creation
+// order (forward then reverse) and their stored directions follow.  S == T collapses to one
+// directed edge with twice the count.
+struct EdgeSlot {
+    unsigned long long key;  // lo << 32 | hi << 1 | (rel > 0)
+    unsigned long long ord;
+    unsigned int cov;  // pair events - 1
+    unsigned int pad[3];
+};
+static_assert(sizeof(EdgeSlot) == 32, "EdgeSlot must be 32 bytes");
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+}  // namespace amira

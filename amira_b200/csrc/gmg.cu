@@ -1,0 +1,812 @@
+// gmg.cu -- the handle, the build / filter pipelines and the C ABI of libamira_gmg.so.
+// See include/amira_gmg.h for the contract and gmg_kernels.cuh for the kernels.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "gmg_kernels.cuh"
+
+namespace amira {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace amira
+
+using namespace amira;
+
+struct amira_gmg {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_sm = 148;
+    int insert_ctas_per_sm = 1;
+
+    // input (owned copy or borrowed device pointers)
+    DevBuf d_ids, d_off, d_ps, d_pe;
+    const int32_t *ids = nullptr;
+    const int64_t *off = nullptr;
+    const int32_t *ps = nullptr, *pe = nullptr;
+    int64_t R = 0, G = 0;
+    int k = 0;
+    bool has_pos = false;
+
+    // per read / per tile
+    DevBuf win_off, is_short, to_correct, tile_r0;
+    // per window
+    DevBuf win_node, win_dir, win_read, win_start, win_end;
+    // hash tables + first-seen bitmaps
+    DevBuf ntab, etab, bitmaps, cnt_node, cnt_edge;
+    unsigned int ncap = 0, ecap = 0;
+    int64_t hint_nodes = 0, hint_edges = 0;
+    // nodes (cur) and compaction targets (alt)
+    DevBuf node_key, node_cov, node_dir, node_comp, reads_off, reads;
+    DevBuf node_key2, node_cov2, node_dir2, node_comp2, reads_off2, reads2;
+    DevBuf parent, is_root;
+    // edges
+    DevBuf e_src, e_tgt, e_sd, e_td, e_cov;
+    DevBuf e_src2, e_tgt2, e_sd2, e_td2, e_cov2;
+    // adjacency: adj_off[2N+1] (forward lists of all nodes, then backward lists), adj_edges[E]
+    DevBuf adj_off, adj_edges, adj_keys, adj_keys2, adj_vals;
+    // scratch
+    DevBuf sort_keys, sort_vals, flags, dups, cub_temp, keep_n, keep_e, comp_max, scratch_off;
+    DevBuf d_status, d_sizes, d_nsel;
+    int *h_status = nullptr;       // pinned
+    long long *h_sizes = nullptr;  // pinned
+
+    int64_t n_nodes = 0, n_edges = 0, W = 0, n_inc = 0, n_short = 0, n_fw = 0, n_bw = 0, n_comps = 0;
+    bool built = false;
+    bool sizes_dirty = false;  // n_inc / n_fw still have to be fetched
+    int last_status = AMIRA_OK;
+
+    bool profiling = false;
+    cudaEvent_t ev[AMIRA_PH_COUNT][2] = {};
+    bool ev_used[AMIRA_PH_COUNT] = {};
+    int64_t launches = 0;      // hand-written kernels launched
+    int64_t lib_launches = 0;  // CUB / memset / memcpy calls
+
+    // multi-GPU
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    int64_t first_read_global = 0, first_call_global = 0;
+};
+
+namespace {
+
+inline int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+struct Phase {
+    amira_gmg *h;
+    int ph;
+    Phase(amira_gmg *h_, int ph_) : h(h_), ph(ph_) {
+        if (h->profiling) {
+            cudaEventRecord(h->ev[ph][0], h->stream);
+            h->ev_used[ph] = true;
+        }
+    }
+    ~Phase() {
+        if (h->profiling) cudaEventRecord(h->ev[ph][1], h->stream);
+    }
+};
+
+#define LAUNCH(h, kern, grid, block, ...)                              \
+    do {                                                               \
+        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);        \
+        (h)->launches++;                                               \
+        AMIRA_CUDA(cudaGetLastError());                                \
+    } while (0)
+
+template <typename F>
+int cub_call(amira_gmg *h, F f) {
+    size_t bytes = 0;
+    AMIRA_CUDA(f(nullptr, bytes));
+    AMIRA_TRY(h->cub_temp.reserve(bytes ? bytes : 1));
+    AMIRA_CUDA(f(h->cub_temp.p, bytes));
+    h->lib_launches++;
+    return AMIRA_OK;
+}
+
+template <typename T>
+int exclusive_sum_inplace(amira_gmg *h, T *data, int64_t n) {
+    return cub_call(h, [&](void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum(t, b, data, data, n, h->stream); });
+}
+
+int bits_for(int64_t n) {
+    int b = 1;
+    while (b < 32 && (1ll << b) < n) ++b;
+    return b;
+}
+
+int fetch_status_sizes(amira_gmg *h) {
+    AMIRA_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    AMIRA_CUDA(cudaMemcpyAsync(h->h_sizes, h->d_sizes.p, sizeof(long long) * SZ_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
+}
+
+void reset_graph(amira_gmg *h) {
+    h->n_nodes = h->n_edges = h->W = h->n_inc = h->n_short = h->n_fw = h->n_bw = h->n_comps = 0;
+    h->sizes_dirty = false;
+}
+
+// node -> forward/backward edge CSR from the current edge arrays
+int build_adjacency(amira_gmg *h) {
+    Phase ph(h, AMIRA_PH_ADJACENCY);
+    const int64_t N = h->n_nodes, E = h->n_edges;
+    AMIRA_TRY(h->adj_off.reserve(sizeof(int64_t) * (2 * N + 2)));
+    AMIRA_CUDA(cudaMemsetAsync(h->adj_off.p, 0, sizeof(int64_t) * (2 * N + 2), h->stream));
+    if (E > 0) {
+        AMIRA_TRY(h->adj_keys.reserve(sizeof(uint32_t) * E));
+        AMIRA_TRY(h->adj_keys2.reserve(sizeof(uint32_t) * E));
+        AMIRA_TRY(h->adj_vals.reserve(sizeof(int32_t) * E));
+        AMIRA_TRY(h->adj_edges.reserve(sizeof(int32_t) * E));
+        LAUNCH(h, k_adj_keys, grid_for(E, 256), 256, h->e_src.as<int32_t>(), h->e_sd.as<int8_t>(), E, N,
+               h->adj_keys.as<uint32_t>(), h->adj_vals.as<int32_t>(), h->adj_off.as<int64_t>());
+        const int bits = bits_for(2 * N + 1);
+        AMIRA_TRY(cub_call(h, [&](void *t, size_t &b) {
+            return cub::DeviceRadixSort::SortPairs(t, b, h->adj_keys.as<uint32_t>(), h->adj_keys2.as<uint32_t>(),
+                                                   h->adj_vals.as<int32_t>(), h->adj_edges.as<int32_t>(), E, 0, bits,
+                                                   h->stream);
+        }));
+    }
+    AMIRA_TRY(exclusive_sum_inplace(h, h->adj_off.as<int64_t>(), 2 * N + 1));
+    h->sizes_dirty = true;
+    return AMIRA_OK;
+}
+
+int finish_sizes(amira_gmg *h) {
+    if (!h->sizes_dirty) return AMIRA_OK;
+    // n_fw = adj_off[N]; n_inc = reads_off[N]
+    int64_t v[2] = {0, 0};
+    AMIRA_CUDA(cudaMemcpyAsync(&v[0], h->adj_off.as<int64_t>() + h->n_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                               h->stream));
+    AMIRA_CUDA(cudaMemcpyAsync(&v[1], h->reads_off.as<int64_t>() + h->n_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                               h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    h->n_fw = v[0];
+    h->n_bw = h->n_edges - v[0];
+    h->n_inc = v[1];
+    h->sizes_dirty = false;
+    return AMIRA_OK;
+}
+
+int alloc_window_arrays(amira_gmg *h) {
+    const int64_t cap = std::max<int64_t>(h->G, 1);
+    AMIRA_TRY(h->win_node.reserve(sizeof(int32_t) * cap));
+    AMIRA_TRY(h->win_dir.reserve(cap));
+    AMIRA_TRY(h->win_read.reserve(sizeof(int32_t) * cap));
+    if (h->has_pos) {
+        AMIRA_TRY(h->win_start.reserve(sizeof(int32_t) * cap));
+        AMIRA_TRY(h->win_end.reserve(sizeof(int32_t) * cap));
+    }
+    return AMIRA_OK;
+}
+
+int do_build(amira_gmg *h) {
+    const int64_t R = h->R, G = h->G;
+    const int k = h->k;
+    cudaStream_t st = h->stream;
+    const int64_t n_tiles = (G + INS_TILE - 1) / INS_TILE;
+    const int64_t n_words = (G + 31) / 32;
+
+    AMIRA_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int) * ST_COUNT, st));
+    AMIRA_CUDA(cudaMemsetAsync(h->d_sizes.p, 0, sizeof(long long) * SZ_COUNT, st));
+    {
+        Phase ph(h, AMIRA_PH_WINDOWS);
+        AMIRA_TRY(h->win_off.reserve(sizeof(int64_t) * (R + 1)));
+        AMIRA_TRY(h->is_short.reserve(R + 1));
+        AMIRA_TRY(h->to_correct.reserve(R + 1));
+        AMIRA_TRY(h->tile_r0.reserve(sizeof(int32_t) * (n_tiles + 1)));
+        LAUNCH(h, k_read_windows, grid_for(R + 1, 256), 256, h->off, R, k, G, h->win_off.as<int64_t>(),
+               h->is_short.as<uint8_t>(), h->to_correct.as<uint8_t>(), h->tile_r0.as<int32_t>(),
+               h->d_sizes.as<long long>(), h->d_status.as<int>());
+        AMIRA_TRY(exclusive_sum_inplace(h, h->win_off.as<int64_t>(), R + 1));
+    }
+    AMIRA_TRY(alloc_window_arrays(h));
+    AMIRA_TRY(h->bitmaps.reserve(sizeof(unsigned int) * 3 * (n_words + 1)));
+    AMIRA_TRY(h->cnt_node.reserve(sizeof(int) * (n_words + 1)));
+    AMIRA_TRY(h->cnt_edge.reserve(sizeof(int) * (n_words + 1)));
+    unsigned int *bm_node = h->bitmaps.as<unsigned int>();
+    unsigned int *bm_ea = bm_node + (n_words + 1), *bm_eb = bm_ea + (n_words + 1);
+
+    // ---- hash tables: sized from hints or from the call count; retried larger on overflow
+    int64_t ncap = h->hint_nodes > 0 ? h->hint_nodes * 2 + 1024 : std::max<int64_t>(4096, G / 4);
+    int64_t ecap = h->hint_edges > 0 ? h->hint_edges * 2 + 1024 : std::max<int64_t>(4096, G / 4);
+    for (int attempt = 0;; ++attempt) {
+        ncap = std::min<int64_t>(ncap, 0x7FFFFFF0ll);
+        ecap = std::min<int64_t>(ecap, 0x7FFFFFF0ll);
+        h->ncap = (unsigned int)ncap;
+        h->ecap = (unsigned int)ecap;
+        AMIRA_TRY(h->ntab.reserve(sizeof(NodeSlot) * ncap));
+        AMIRA_TRY(h->etab.reserve(sizeof(EdgeSlot) * ecap));
+        {
+            Phase ph(h, AMIRA_PH_INSERT);
+            AMIRA_CUDA(cudaMemsetAsync(h->ntab.p, 0xFF, sizeof(NodeSlot) * ncap, st));
+            AMIRA_CUDA(cudaMemsetAsync(h->etab.p, 0xFF, sizeof(EdgeSlot) * ecap, st));
+            h->lib_launches += 2;
+            if (n_tiles > 0) {
+                BuildParams P;
+                P.ids = h->ids; P.off = h->off; P.win_off = h->win_off.as<int64_t>();
+                P.tile_r0 = h->tile_r0.as<int32_t>(); P.ps = h->ps; P.pe = h->pe;
+                P.G = G; P.R = R; P.n_tiles = n_tiles; P.k = k;
+                P.ntab = h->ntab.as<NodeSlot>(); P.ncap = h->ncap; P.etab = h->etab.as<EdgeSlot>(); P.ecap = h->ecap;
+                P.win_node = h->win_node.as<int32_t>(); P.win_dir = h->win_dir.as<int8_t>();
+                P.win_read = h->win_read.as<int32_t>();
+                P.win_start = h->has_pos ? h->win_start.as<int32_t>() : nullptr;
+                P.win_end = h->has_pos ? h->win_end.as<int32_t>() : nullptr;
+                P.status = h->d_status.as<int>();
+                P.read_base = h->first_read_global;
+                const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sm * h->insert_ctas_per_sm);
+                LAUNCH(h, k_insert_windows, grid, INS_THREADS, P);
+            }
+        }
+        {
+            Phase ph(h, AMIRA_PH_ORDER);
+            AMIRA_CUDA(cudaMemsetAsync(h->bitmaps.p, 0, sizeof(unsigned int) * 3 * (n_words + 1), st));
+            const unsigned int tmax = std::max(h->ncap, h->ecap);
+            LAUNCH(h, k_mark_first, std::min<int>(grid_for(tmax, 256), h->n_sm * 16), 256, h->ntab.as<NodeSlot>(), h->ncap,
+                   h->etab.as<EdgeSlot>(), h->ecap, bm_node, bm_ea, bm_eb);
+            LAUNCH(h, k_popcount, grid_for(n_words + 1, 256), 256, bm_node, bm_ea, bm_eb, n_words, h->cnt_node.as<int>(),
+                   h->cnt_edge.as<int>());
+            AMIRA_TRY(exclusive_sum_inplace(h, h->cnt_node.as<int>(), n_words + 1));
+            AMIRA_TRY(exclusive_sum_inplace(h, h->cnt_edge.as<int>(), n_words + 1));
+            LAUNCH(h, k_collect_sizes, 1, 32, h->win_off.as<int64_t>(), R, h->cnt_node.as<int>(), h->cnt_edge.as<int>(),
+                   n_words, h->d_sizes.as<long long>());
+        }
+        AMIRA_TRY(fetch_status_sizes(h));
+        if (h->h_status[ST_ERR]) break;
+        const bool ovn = h->h_status[ST_OVERFLOW_N], ove = h->h_status[ST_OVERFLOW_E];
+        if (!ovn && !ove) break;
+        if (attempt >= 6) {
+            set_error("hash tables overflowed after %d attempts (ncap=%lld ecap=%lld)", attempt + 1, (long long)ncap,
+                      (long long)ecap);
+            return AMIRA_E_NOMEM;
+        }
+        if (ovn) ncap *= 4;
+        if (ove) ecap *= 4;
+        AMIRA_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int) * ST_COUNT, st));
+        long long keep_short = h->h_sizes[SZ_SHORT];
+        AMIRA_CUDA(cudaMemsetAsync(h->d_sizes.p, 0, sizeof(long long) * SZ_COUNT, st));
+        AMIRA_CUDA(cudaMemcpyAsync(h->d_sizes.as<long long>() + SZ_SHORT, &keep_short, sizeof(long long),
+                                   cudaMemcpyHostToDevice, st));
+        AMIRA_CUDA(cudaStreamSynchronize(st));
+    }
+    h->n_short = h->h_sizes[SZ_SHORT];
+    if (h->h_status[ST_ERR]) {
+        const int e = h->h_status[ST_ERR];
+        if (e == AMIRA_E_PALINDROME) set_error("Gene-mer and reverse complement gene-mer are identical");
+        else set_error("invalid read offsets");
+        return e;
+    }
+    h->W = h->h_sizes[SZ_W];
+    h->n_nodes = h->h_sizes[SZ_NODES];
+    h->n_edges = h->h_sizes[SZ_EDGES];
+    const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
+
+    // ---- node / edge arrays in first-seen order, union-find on the way
+    {
+        Phase ph(h, AMIRA_PH_EMIT);
+        AMIRA_TRY(h->node_key.reserve(sizeof(int32_t) * std::max<int64_t>(1, N * k)));
+        AMIRA_TRY(h->node_cov.reserve(sizeof(uint32_t) * (N + 1)));
+        AMIRA_TRY(h->node_dir.reserve(N + 1));
+        AMIRA_TRY(h->node_comp.reserve(sizeof(uint32_t) * (N + 1)));
+        AMIRA_TRY(h->parent.reserve(sizeof(int32_t) * (N + 1)));
+        AMIRA_TRY(h->is_root.reserve(sizeof(int) * (N + 2)));
+        AMIRA_TRY(h->e_src.reserve(sizeof(int32_t) * (E + 1)));
+        AMIRA_TRY(h->e_tgt.reserve(sizeof(int32_t) * (E + 1)));
+        AMIRA_TRY(h->e_sd.reserve(E + 1));
+        AMIRA_TRY(h->e_td.reserve(E + 1));
+        AMIRA_TRY(h->e_cov.reserve(sizeof(uint32_t) * (E + 1)));
+        if (N > 0) {
+            LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->ntab.as<NodeSlot>(), h->ncap,
+                   h->ids, k, bm_node, h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
+                   h->node_dir.as<int8_t>(), h->parent.as<int32_t>());
+        }
+        if (E > 0) {
+            LAUNCH(h, k_emit_edges, std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16), 256, h->etab.as<EdgeSlot>(), h->ecap,
+                   h->ntab.as<NodeSlot>(), bm_ea, bm_eb, h->cnt_edge.as<int>(), h->e_src.as<int32_t>(),
+                   h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(), h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(),
+                   h->parent.as<int32_t>());
+        }
+    }
+    // ---- per-read node lists: slot -> node index
+    if (W > 0) {
+        Phase ph(h, AMIRA_PH_REMAP);
+        LAUNCH(h, k_remap_windows, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->ntab.as<NodeSlot>(),
+               h->win_node.as<int32_t>(), W);
+    }
+    // ---- node -> reads
+    {
+        Phase ph(h, AMIRA_PH_INCIDENCE);
+        AMIRA_TRY(h->reads_off.reserve(sizeof(int64_t) * (N + 2)));
+        AMIRA_TRY(h->reads.reserve(sizeof(int32_t) * std::max<int64_t>(1, W)));
+        AMIRA_TRY(h->dups.reserve(sizeof(uint32_t) * (N + 1)));
+        AMIRA_CUDA(cudaMemsetAsync(h->dups.p, 0, sizeof(uint32_t) * (N + 1), st));
+        if (W > 0) {
+            AMIRA_TRY(h->sort_keys.reserve(sizeof(int32_t) * W));
+            AMIRA_TRY(h->sort_vals.reserve(sizeof(int32_t) * W));
+            AMIRA_TRY(h->flags.reserve(W));
+            const int bits = bits_for(N);
+            AMIRA_TRY(cub_call(h, [&](void *t, size_t &b) {
+                return cub::DeviceRadixSort::SortPairs(t, b, h->win_node.as<uint32_t>(), h->sort_keys.as<uint32_t>(),
+                                                       h->win_read.as<int32_t>(), h->sort_vals.as<int32_t>(), W, 0, bits, st);
+            }));
+            LAUNCH(h, k_incidence_flags, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->sort_keys.as<int32_t>(),
+                   h->sort_vals.as<int32_t>(), W, h->flags.as<uint8_t>(), h->dups.as<uint32_t>());
+            AMIRA_TRY(cub_call(h, [&](void *t, size_t &b) {
+                return cub::DeviceSelect::Flagged(t, b, h->sort_vals.as<int32_t>(), h->flags.as<uint8_t>(),
+                                                  h->reads.as<int32_t>(), h->d_nsel.as<long long>(), W, st);
+            }));
+        }
+        LAUNCH(h, k_incidence_counts, grid_for(N + 1, 256), 256, h->node_cov.as<uint32_t>(), h->dups.as<uint32_t>(), N,
+               h->reads_off.as<int64_t>());
+        AMIRA_TRY(exclusive_sum_inplace(h, h->reads_off.as<int64_t>(), N + 1));
+    }
+    AMIRA_TRY(build_adjacency(h));
+    // ---- components
+    {
+        Phase ph(h, AMIRA_PH_COMPONENTS);
+        LAUNCH(h, k_cc_roots, grid_for(N + 1, 256), 256, h->parent.as<int32_t>(), N, h->is_root.as<int>());
+        AMIRA_TRY(exclusive_sum_inplace(h, h->is_root.as<int>(), N + 1));
+        if (N > 0)
+            LAUNCH(h, k_cc_number, grid_for(N, 256), 256, h->parent.as<int32_t>(), h->is_root.as<int>(), N,
+                   h->node_comp.as<uint32_t>());
+    }
+    h->n_comps = N;  // upper bound on component ids (ids are <= number of nodes)
+    h->sizes_dirty = true;
+    return AMIRA_OK;
+}
+
+int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
+    if (!h->built) {
+        set_error("filter before build");
+        return AMIRA_E_STATE;
+    }
+    AMIRA_TRY(finish_sizes(h));
+    const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
+    const int k = h->k;
+    cudaStream_t st = h->stream;
+    if (N == 0) return AMIRA_OK;
+    Phase ph(h, AMIRA_PH_FILTER);
+    AMIRA_TRY(h->keep_n.reserve(sizeof(int) * 2 * (N + 2)));
+    AMIRA_TRY(h->keep_e.reserve(sizeof(int) * 2 * (E + 2)));
+    int *keep_n = h->keep_n.as<int>(), *new_n = keep_n + (N + 2);
+    int *keep_e = h->keep_e.as<int>(), *new_e = keep_e + (E + 2);
+    if (mode == 1) {
+        AMIRA_TRY(h->comp_max.reserve(sizeof(uint32_t) * (h->n_comps + 2)));
+        AMIRA_CUDA(cudaMemsetAsync(h->comp_max.p, 0, sizeof(uint32_t) * (h->n_comps + 2), st));
+        LAUNCH(h, k_component_max, grid_for(N, 256), 256, h->node_cov.as<uint32_t>(), h->node_comp.as<uint32_t>(), N,
+               h->comp_max.as<uint32_t>());
+    }
+    LAUNCH(h, k_node_keep, grid_for(N + 1, 256), 256, h->node_cov.as<uint32_t>(), h->node_comp.as<uint32_t>(),
+           h->comp_max.as<uint32_t>(), N, thr_node, mode, keep_n);
+    if (mode == 1 && E > 0) {
+        AMIRA_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int) * ST_COUNT, st));
+        LAUNCH(h, k_multi_edge_check, grid_for(N, 256), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(),
+               h->adj_edges.as<int32_t>(), h->adj_off.as<int64_t>(), keep_n, N, h->d_status.as<int>());
+        AMIRA_TRY(fetch_status_sizes(h));
+        if (h->h_status[ST_ERR] == AMIRA_E_MULTI_EDGE) {
+            set_error("unhashable type: 'list'");
+            return AMIRA_E_MULTI_EDGE;
+        }
+    }
+    LAUNCH(h, k_edge_keep, grid_for(E + 1, 256), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(),
+           h->e_cov.as<uint32_t>(), keep_n, E, thr_edge, keep_e);
+    AMIRA_CUDA(cudaMemcpyAsync(new_n, keep_n, sizeof(int) * (N + 1), cudaMemcpyDeviceToDevice, st));
+    AMIRA_CUDA(cudaMemcpyAsync(new_e, keep_e, sizeof(int) * (E + 1), cudaMemcpyDeviceToDevice, st));
+    AMIRA_TRY(exclusive_sum_inplace(h, new_n, N + 1));
+    AMIRA_TRY(exclusive_sum_inplace(h, new_e, E + 1));
+    LAUNCH(h, k_filter_sizes, 1, 32, new_n, N, new_e, E, h->d_sizes.as<long long>());
+
+    AMIRA_TRY(h->node_key2.reserve(sizeof(int32_t) * std::max<int64_t>(1, N * k)));
+    AMIRA_TRY(h->node_cov2.reserve(sizeof(uint32_t) * (N + 1)));
+    AMIRA_TRY(h->node_dir2.reserve(N + 1));
+    AMIRA_TRY(h->node_comp2.reserve(sizeof(uint32_t) * (N + 1)));
+    AMIRA_TRY(h->reads_off2.reserve(sizeof(int64_t) * (N + 2)));
+    AMIRA_TRY(h->reads2.reserve(sizeof(int32_t) * std::max<int64_t>(1, h->n_inc)));
+    LAUNCH(h, k_compact_nodes, grid_for(N, 256), 256, keep_n, new_n, N, k, h->node_key.as<int32_t>(),
+           h->node_cov.as<uint32_t>(), h->node_dir.as<int8_t>(), h->node_comp.as<uint32_t>(), h->reads_off.as<int64_t>(),
+           h->node_key2.as<int32_t>(), h->node_cov2.as<uint32_t>(), h->node_dir2.as<int8_t>(),
+           h->node_comp2.as<uint32_t>(), h->reads_off2.as<int64_t>());
+    // sizes are needed on the host to scan exactly new_N + 1 read counts
+    AMIRA_TRY(fetch_status_sizes(h));
+    const int64_t N2 = h->h_sizes[SZ_NODES], E2 = h->h_sizes[SZ_EDGES];
+    AMIRA_TRY(exclusive_sum_inplace(h, h->reads_off2.as<int64_t>(), N2 + 1));
+    LAUNCH(h, k_compact_incidence, grid_for(N * 32, 256), 256, keep_n, new_n, N, h->reads_off.as<int64_t>(),
+           h->reads.as<int32_t>(), h->reads_off2.as<int64_t>(), h->reads2.as<int32_t>());
+    if (E > 0) {
+        AMIRA_TRY(h->e_src2.reserve(sizeof(int32_t) * (E + 1)));
+        AMIRA_TRY(h->e_tgt2.reserve(sizeof(int32_t) * (E + 1)));
+        AMIRA_TRY(h->e_sd2.reserve(E + 1));
+        AMIRA_TRY(h->e_td2.reserve(E + 1));
+        AMIRA_TRY(h->e_cov2.reserve(sizeof(uint32_t) * (E + 1)));
+        LAUNCH(h, k_compact_edges, grid_for(E, 256), 256, keep_e, new_e, new_n, E, h->e_src.as<int32_t>(),
+               h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(), h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(),
+               h->e_src2.as<int32_t>(), h->e_tgt2.as<int32_t>(), h->e_sd2.as<int8_t>(), h->e_td2.as<int8_t>(),
+               h->e_cov2.as<uint32_t>());
+    }
+    if (W > 0) {
+        LAUNCH(h, k_mask_windows, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, keep_n, new_n,
+               h->win_node.as<int32_t>(), h->win_dir.as<int8_t>(), h->win_read.as<int32_t>(),
+               h->has_pos ? h->win_start.as<int32_t>() : nullptr, h->has_pos ? h->win_end.as<int32_t>() : nullptr, W,
+               h->to_correct.as<uint8_t>());
+    }
+    std::swap(h->node_key, h->node_key2);
+    std::swap(h->node_cov, h->node_cov2);
+    std::swap(h->node_dir, h->node_dir2);
+    std::swap(h->node_comp, h->node_comp2);
+    std::swap(h->reads_off, h->reads_off2);
+    std::swap(h->reads, h->reads2);
+    if (E > 0) {
+        std::swap(h->e_src, h->e_src2);
+        std::swap(h->e_tgt, h->e_tgt2);
+        std::swap(h->e_sd, h->e_sd2);
+        std::swap(h->e_td, h->e_td2);
+        std::swap(h->e_cov, h->e_cov2);
+    }
+    h->n_nodes = N2;
+    h->n_edges = E2;
+    AMIRA_TRY(build_adjacency(h));
+    h->sizes_dirty = true;
+    return AMIRA_OK;
+}
+
+__global__ void k_sub_offset(const int64_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] - in[0];
+}
+
+int d2h(amira_gmg *h, void *dst, const void *src, size_t bytes) {
+    if (!dst || bytes == 0) return AMIRA_OK;
+    AMIRA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    h->lib_launches++;
+    return AMIRA_OK;
+}
+
+int check_handle(const amira_gmg *h) {
+    if (!h) {
+        set_error("null handle");
+        return AMIRA_E_ARG;
+    }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+        return AMIRA_E_CUDA;
+    }
+    return AMIRA_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *amira_last_error(void) { return g_err; }
+const char *amira_version(void) { return "amira_gmg 0.1 (sm_100a)"; }
+
+int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
+    if (!out) return AMIRA_E_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: %s (there is no CPU fallback)", cudaGetErrorString(e));
+        return AMIRA_E_CUDA;
+    }
+    if (device < 0 || device >= n_dev) {
+        set_error("device %d out of range (%d devices)", device, n_dev);
+        return AMIRA_E_ARG;
+    }
+    AMIRA_CUDA(cudaSetDevice(device));
+    amira_gmg *h = new amira_gmg();
+    h->device = device;
+    if (cuda_stream) {
+        h->stream = (cudaStream_t)cuda_stream;
+    } else {
+        AMIRA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    AMIRA_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->n_sm = prop.multiProcessorCount;
+    int occ = 1;
+    AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_insert_windows, INS_THREADS, 0));
+    h->insert_ctas_per_sm = std::max(1, occ);
+    AMIRA_TRY(h->d_status.reserve(sizeof(int) * ST_COUNT));
+    AMIRA_TRY(h->d_sizes.reserve(sizeof(long long) * SZ_COUNT));
+    AMIRA_TRY(h->d_nsel.reserve(sizeof(long long)));
+    AMIRA_CUDA(cudaMallocHost((void **)&h->h_status, sizeof(int) * ST_COUNT));
+    AMIRA_CUDA(cudaMallocHost((void **)&h->h_sizes, sizeof(long long) * SZ_COUNT));
+    for (int i = 0; i < AMIRA_PH_COUNT; ++i)
+        for (int j = 0; j < 2; ++j) AMIRA_CUDA(cudaEventCreate(&h->ev[i][j]));
+    *out = h;
+    return AMIRA_OK;
+}
+
+void amira_gmg_destroy(amira_gmg *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->d_ids, &h->d_off, &h->d_ps, &h->d_pe, &h->win_off, &h->is_short, &h->to_correct, &h->tile_r0,
+                      &h->win_node, &h->win_dir, &h->win_read, &h->win_start, &h->win_end, &h->ntab, &h->etab,
+                      &h->bitmaps, &h->cnt_node, &h->cnt_edge, &h->node_key, &h->node_cov, &h->node_dir, &h->node_comp,
+                      &h->reads_off, &h->reads, &h->node_key2, &h->node_cov2, &h->node_dir2, &h->node_comp2,
+                      &h->reads_off2, &h->reads2, &h->parent, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
+                      &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
+                      &h->adj_keys, &h->adj_keys2, &h->adj_vals, &h->sort_keys, &h->sort_vals, &h->flags, &h->dups,
+                      &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,
+                      &h->d_nsel};
+    for (DevBuf *b : bufs) b->release();
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_sizes) cudaFreeHost(h->h_sizes);
+    for (int i = 0; i < AMIRA_PH_COUNT; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (h->ev[i][j]) cudaEventDestroy(h->ev[i][j]);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int amira_gmg_reserve(amira_gmg *h, int64_t n_nodes_hint, int64_t n_edges_hint) {
+    AMIRA_TRY(check_handle(h));
+    h->hint_nodes = n_nodes_hint;
+    h->hint_edges = n_edges_hint;
+    return AMIRA_OK;
+}
+
+int amira_gmg_set_profiling(amira_gmg *h, int enabled) {
+    AMIRA_TRY(check_handle(h));
+    h->profiling = enabled != 0;
+    return AMIRA_OK;
+}
+
+int amira_gmg_phase_ms(const amira_gmg *h, int phase, float *ms) {
+    if (!h || !ms || phase < 0 || phase >= AMIRA_PH_COUNT) return AMIRA_E_ARG;
+    *ms = 0.f;
+    if (!h->ev_used[phase]) return AMIRA_OK;
+    cudaError_t e = cudaEventElapsedTime(ms, h->ev[phase][0], h->ev[phase][1]);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *ms = 0.f;
+    }
+    return AMIRA_OK;
+}
+
+int amira_gmg_kernel_launches(const amira_gmg *h, int64_t *n) {
+    if (!h || !n) return AMIRA_E_ARG;
+    *n = h->launches;
+    return AMIRA_OK;
+}
+
+int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read_off, int64_t R, int32_t k,
+                    const int32_t *pos_start, const int32_t *pos_end, int input_on_device) {
+    AMIRA_TRY(check_handle(h));
+    h->built = false;
+    reset_graph(h);
+    for (int i = 0; i < AMIRA_PH_COUNT; ++i) h->ev_used[i] = false;
+    if (R < 0 || k < 0 || (R > 0 && !read_off) || ((pos_start == nullptr) != (pos_end == nullptr))) {
+        set_error("bad arguments to amira_gmg_build");
+        return h->last_status = AMIRA_E_ARG;
+    }
+    if (R >= 0x7FFFFFF0ll) {
+        set_error("too many reads for int32 read indices");
+        return h->last_status = AMIRA_E_ARG;
+    }
+    h->R = R;
+    h->k = k;
+    h->has_pos = pos_start != nullptr;
+    h->G = 0;
+    if (R == 0) {  // GeneMerGraph({}, k): empty graph for any k (tests/test_gene_mer_graph.py:14-36)
+        h->built = true;
+        return h->last_status = AMIRA_OK;
+    }
+    if (k == 0) {  // GeneMer([]) for every read: "Gene-mer is empty"
+        set_error("Gene-mer is empty");
+        return h->last_status = AMIRA_E_EMPTY_GENEMER;
+    }
+    if (k > MAX_K) {
+        set_error("k=%d exceeds the supported maximum %d", k, MAX_K);
+        return h->last_status = AMIRA_E_ARG;
+    }
+    cudaStream_t st = h->stream;
+    int64_t G = 0;
+    if (input_on_device) {
+        AMIRA_CUDA(cudaMemcpyAsync(&G, read_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        AMIRA_CUDA(cudaStreamSynchronize(st));
+    } else {
+        G = read_off[R];
+    }
+    if (G < 0 || G >= (1ll << (P_BITS - 1)) || (G > 0 && !signed_ids)) {
+        set_error("bad call count %lld", (long long)G);
+        return h->last_status = AMIRA_E_ARG;
+    }
+    h->G = G;
+    if (input_on_device) {
+        h->ids = signed_ids;
+        h->off = read_off;
+        h->ps = pos_start;
+        h->pe = pos_end;
+    } else {
+        Phase ph(h, AMIRA_PH_H2D);
+        AMIRA_TRY(h->d_ids.reserve(sizeof(int32_t) * std::max<int64_t>(G, 1) + 16));
+        AMIRA_TRY(h->d_off.reserve(sizeof(int64_t) * (R + 1)));
+        if (G > 0) AMIRA_CUDA(cudaMemcpyAsync(h->d_ids.p, signed_ids, sizeof(int32_t) * G, cudaMemcpyHostToDevice, st));
+        AMIRA_CUDA(cudaMemcpyAsync(h->d_off.p, read_off, sizeof(int64_t) * (R + 1), cudaMemcpyHostToDevice, st));
+        h->ids = h->d_ids.as<int32_t>();
+        h->off = h->d_off.as<int64_t>();
+        h->ps = h->pe = nullptr;
+        if (h->has_pos) {
+            AMIRA_TRY(h->d_ps.reserve(sizeof(int32_t) * std::max<int64_t>(G, 1)));
+            AMIRA_TRY(h->d_pe.reserve(sizeof(int32_t) * std::max<int64_t>(G, 1)));
+            if (G > 0) {
+                AMIRA_CUDA(cudaMemcpyAsync(h->d_ps.p, pos_start, sizeof(int32_t) * G, cudaMemcpyHostToDevice, st));
+                AMIRA_CUDA(cudaMemcpyAsync(h->d_pe.p, pos_end, sizeof(int32_t) * G, cudaMemcpyHostToDevice, st));
+            }
+            h->ps = h->d_ps.as<int32_t>();
+            h->pe = h->d_pe.as<int32_t>();
+        }
+        h->lib_launches += 2;
+    }
+    int rc = do_build(h);
+    h->last_status = rc;
+    h->built = (rc == AMIRA_OK);
+    return rc;
+}
+
+int amira_gmg_sync(amira_gmg *h) {
+    AMIRA_TRY(check_handle(h));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return h->last_status;
+}
+
+int amira_gmg_sizes(amira_gmg *h, int64_t *n_nodes, int64_t *n_edges, int64_t *n_windows, int64_t *n_incidence,
+                    int64_t *n_fw, int64_t *n_bw, int64_t *n_short) {
+    AMIRA_TRY(check_handle(h));
+    if (!h->built) {
+        set_error("sizes before a successful build");
+        return AMIRA_E_STATE;
+    }
+    AMIRA_TRY(finish_sizes(h));
+    if (n_nodes) *n_nodes = h->n_nodes;
+    if (n_edges) *n_edges = h->n_edges;
+    if (n_windows) *n_windows = h->W;
+    if (n_incidence) *n_incidence = h->n_inc;
+    if (n_fw) *n_fw = h->n_fw;
+    if (n_bw) *n_bw = h->n_bw;
+    if (n_short) *n_short = h->n_short;
+    return AMIRA_OK;
+}
+
+int amira_gmg_export_nodes(amira_gmg *h, int32_t *key, uint32_t *cov, int8_t *first_dir, uint32_t *component,
+                           int64_t *reads_off, int32_t *reads, int64_t *fw_off, int32_t *fw_edges, int64_t *bw_off,
+                           int32_t *bw_edges) {
+    AMIRA_TRY(check_handle(h));
+    if (!h->built) {
+        set_error("export before a successful build");
+        return AMIRA_E_STATE;
+    }
+    AMIRA_TRY(finish_sizes(h));
+    const int64_t N = h->n_nodes;
+    if (N == 0 || h->R == 0) {
+        if (reads_off) reads_off[0] = 0;
+        if (fw_off) fw_off[0] = 0;
+        if (bw_off) bw_off[0] = 0;
+        return AMIRA_OK;
+    }
+    AMIRA_TRY(d2h(h, key, h->node_key.p, sizeof(int32_t) * N * h->k));
+    AMIRA_TRY(d2h(h, cov, h->node_cov.p, sizeof(uint32_t) * N));
+    AMIRA_TRY(d2h(h, first_dir, h->node_dir.p, N));
+    AMIRA_TRY(d2h(h, component, h->node_comp.p, sizeof(uint32_t) * N));
+    AMIRA_TRY(d2h(h, reads_off, h->reads_off.p, sizeof(int64_t) * (N + 1)));
+    AMIRA_TRY(d2h(h, reads, h->reads.p, sizeof(int32_t) * h->n_inc));
+    AMIRA_TRY(d2h(h, fw_off, h->adj_off.p, sizeof(int64_t) * (N + 1)));
+    AMIRA_TRY(d2h(h, fw_edges, h->adj_edges.p, sizeof(int32_t) * h->n_fw));
+    if (bw_off) {
+        AMIRA_TRY(h->scratch_off.reserve(sizeof(int64_t) * (N + 1)));
+        LAUNCH(h, k_sub_offset, grid_for(N + 1, 256), 256, h->adj_off.as<int64_t>() + N, N + 1,
+               h->scratch_off.as<int64_t>());
+        AMIRA_TRY(d2h(h, bw_off, h->scratch_off.p, sizeof(int64_t) * (N + 1)));
+    }
+    AMIRA_TRY(d2h(h, bw_edges, h->adj_edges.as<int32_t>() + h->n_fw, sizeof(int32_t) * h->n_bw));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
+}
+
+int amira_gmg_export_edges(amira_gmg *h, int32_t *src, int32_t *tgt, int8_t *sd, int8_t *td, uint32_t *cov) {
+    AMIRA_TRY(check_handle(h));
+    if (!h->built) {
+        set_error("export before a successful build");
+        return AMIRA_E_STATE;
+    }
+    const int64_t E = h->n_edges;
+    if (E == 0) return AMIRA_OK;
+    AMIRA_TRY(d2h(h, src, h->e_src.p, sizeof(int32_t) * E));
+    AMIRA_TRY(d2h(h, tgt, h->e_tgt.p, sizeof(int32_t) * E));
+    AMIRA_TRY(d2h(h, sd, h->e_sd.p, E));
+    AMIRA_TRY(d2h(h, td, h->e_td.p, E));
+    AMIRA_TRY(d2h(h, cov, h->e_cov.p, sizeof(uint32_t) * E));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
+}
+
+int amira_gmg_export_reads(amira_gmg *h, int64_t *win_off, int32_t *node_idx, int8_t *dir, int32_t *start,
+                           int32_t *end, uint8_t *is_short, uint8_t *to_correct) {
+    AMIRA_TRY(check_handle(h));
+    if (!h->built) {
+        set_error("export before a successful build");
+        return AMIRA_E_STATE;
+    }
+    if (h->R == 0) {
+        if (win_off) win_off[0] = 0;
+        return AMIRA_OK;
+    }
+    if ((start || end) && !h->has_pos) {
+        set_error("positions requested but none were supplied to the build");
+        return AMIRA_E_STATE;
+    }
+    const int64_t W = h->W, R = h->R;
+    AMIRA_TRY(d2h(h, win_off, h->win_off.p, sizeof(int64_t) * (R + 1)));
+    AMIRA_TRY(d2h(h, node_idx, h->win_node.p, sizeof(int32_t) * W));
+    AMIRA_TRY(d2h(h, dir, h->win_dir.p, W));
+    AMIRA_TRY(d2h(h, start, h->win_start.p, sizeof(int32_t) * W));
+    AMIRA_TRY(d2h(h, end, h->win_end.p, sizeof(int32_t) * W));
+    AMIRA_TRY(d2h(h, is_short, h->is_short.p, R));
+    AMIRA_TRY(d2h(h, to_correct, h->to_correct.p, R));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
+}
+
+int amira_gmg_remove_low_coverage_components(amira_gmg *h, uint32_t min_component_cov) {
+    AMIRA_TRY(check_handle(h));
+    return h->last_status = do_filter(h, 1, min_component_cov, 0);
+}
+
+int amira_gmg_filter(amira_gmg *h, uint32_t min_node_cov, uint32_t min_edge_cov) {
+    AMIRA_TRY(check_handle(h));
+    return h->last_status = do_filter(h, 0, min_node_cov, min_edge_cov);
+}
+
+int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, double *red_add_per_s, double *cas_per_s) {
+    AMIRA_TRY(check_handle(h));
+    if (table_bytes < 64 || n_ops < 1) return AMIRA_E_ARG;
+    DevBuf t;
+    AMIRA_TRY(t.reserve((size_t)table_bytes));
+    cudaEvent_t a, b;
+    AMIRA_CUDA(cudaEventCreate(&a));
+    AMIRA_CUDA(cudaEventCreate(&b));
+    const int grid = h->n_sm * 8;
+    float ms = 0.f;
+    for (int which = 0; which < 2; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            AMIRA_CUDA(cudaMemsetAsync(t.p, 0xFF, (size_t)table_bytes, h->stream));
+            AMIRA_CUDA(cudaEventRecord(a, h->stream));
+            if (which == 0)
+                LAUNCH(h, k_atomic_red, grid, 256, t.as<unsigned int>(), (unsigned long long)(table_bytes / 4),
+                       (unsigned long long)n_ops, 0x1234ull + rep);
+            else
+                LAUNCH(h, k_atomic_cas, grid, 256, t.as<unsigned long long>(), (unsigned long long)(table_bytes / 8),
+                       (unsigned long long)n_ops, 0x1234ull + rep);
+            AMIRA_CUDA(cudaEventRecord(b, h->stream));
+            AMIRA_CUDA(cudaEventSynchronize(b));
+            AMIRA_CUDA(cudaEventElapsedTime(&ms, a, b));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        double rate = (double)n_ops / (best * 1e-3);
+        if (which == 0 && red_add_per_s) *red_add_per_s = rate;
+        if (which == 1 && cas_per_s) *cas_per_s = rate;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    t.release();
+    return AMIRA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""Thin object over the C-ABI handle: integer CSR in, graph arrays out.
+
+This is the level the parity tests and bench.py drive: it makes exactly the calls a maintainer's
+ctypes stub would make and returns the exported arrays unchanged."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):      # torch tensor (host pinned or device)
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+class DeviceGraph:
+    """one GeneMerGraph build resident on one GPU"""
+
+    def __init__(self, device: int = 0, stream: int | None = None, profiling: bool = False):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.amira_gmg_create(C.byref(self._h), int(device), C.c_void_p(stream) if stream else None))
+        self.device = device
+        self.k = None
+        self.R = 0
+        self.has_pos = False
+        self._keep = None
+        if profiling:
+            self.set_profiling(True)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.amira_gmg_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_profiling(self, on: bool):
+        _lib.check(self._lib.amira_gmg_set_profiling(self._h, int(on)))
+
+    def reserve(self, n_nodes: int, n_edges: int):
+        _lib.check(self._lib.amira_gmg_reserve(self._h, int(n_nodes), int(n_edges)))
+
+    def build(self, ids, off, k: int, pos_start=None, pos_end=None, on_device: bool = False):
+        """amira_gmg_build; ids/off are numpy arrays, torch tensors or raw pointers"""
+        if isinstance(ids, np.ndarray):
+            ids = np.ascontiguousarray(ids, np.int32)
+            off = np.ascontiguousarray(off, np.int64)
+            if pos_start is not None:
+                pos_start = np.ascontiguousarray(pos_start, np.int32)
+                pos_end = np.ascontiguousarray(pos_end, np.int32)
+        R = (off.shape[0] if hasattr(off, "shape") else len(off)) - 1
+        self._keep = (ids, off, pos_start, pos_end)   # borrowed by the library until the next build
+        self.k, self.R, self.has_pos = int(k), int(R), pos_start is not None
+        _lib.check(self._lib.amira_gmg_build(self._h, _ptr(ids), _ptr(off), R, int(k), _ptr(pos_start), _ptr(pos_end),
+                                             int(on_device)))
+        return self
+
+    def sync(self):
+        _lib.check(self._lib.amira_gmg_sync(self._h))
+
+    def filter_graph(self, min_node_cov: int, min_edge_cov: int):
+        _lib.check(self._lib.amira_gmg_filter(self._h, int(min_node_cov), int(min_edge_cov)))
+        return self
+
+    def remove_low_coverage_components(self, min_component_cov: int):
+        _lib.check(self._lib.amira_gmg_remove_low_coverage_components(self._h, int(min_component_cov)))
+
+    def sizes(self) -> dict:
+        v = [C.c_int64() for _ in range(7)]
+        _lib.check(self._lib.amira_gmg_sizes(self._h, *[C.byref(x) for x in v]))
+        names = ("nodes", "edges", "windows", "incidences", "fw", "bw", "short_reads")
+        return dict(zip(names, (x.value for x in v)))
+
+    def phase_ms(self) -> dict:
+        out = {}
+        for i, name in enumerate(_lib.PHASES):
+            ms = C.c_float()
+            _lib.check(self._lib.amira_gmg_phase_ms(self._h, i, C.byref(ms)))
+            out[name] = ms.value
+        return out
+
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        _lib.check(self._lib.amira_gmg_kernel_launches(self._h, C.byref(n)))
+        return n.value
+
+    def atomic_peak(self, table_bytes: int, n_ops: int):
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self._lib.amira_gmg_atomic_peak(self._h, int(table_bytes), int(n_ops), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def arrays(self, out=None) -> dict:
+        """export every graph array to host memory (numpy); `out` may supply preallocated buffers"""
+        s = self.sizes()
+        n, m, W, R, k = s["nodes"], s["edges"], s["windows"], self.R, self.k
+
+        def buf(name, shape, dtype):
+            if out is not None and name in out:
+                return out[name]
+            return np.empty(shape, dtype)
+
+        a = {
+            "k": np.int32(k),
+            "node_key": buf("node_key", (n, max(k, 0)), np.int32), "node_cov": buf("node_cov", n, np.uint32),
+            "node_dir": buf("node_dir", n, np.int8), "node_comp": buf("node_comp", n, np.uint32),
+            "node_reads_off": buf("node_reads_off", n + 1, np.int64), "node_reads": buf("node_reads", s["incidences"], np.int32),
+            "fw_off": buf("fw_off", n + 1, np.int64), "fw_edges": buf("fw_edges", s["fw"], np.int32),
+            "bw_off": buf("bw_off", n + 1, np.int64), "bw_edges": buf("bw_edges", s["bw"], np.int32),
+            "edge_src": buf("edge_src", m, np.int32), "edge_tgt": buf("edge_tgt", m, np.int32),
+            "edge_sd": buf("edge_sd", m, np.int8), "edge_td": buf("edge_td", m, np.int8), "edge_cov": buf("edge_cov", m, np.uint32),
+            "win_off": buf("win_off", R + 1, np.int64), "win_node": buf("win_node", W, np.int32),
+            "win_dir": buf("win_dir", W, np.int8), "is_short": buf("is_short", R, np.uint8),
+            "to_correct": buf("to_correct", R, np.uint8),
+        }
+        if self.has_pos:
+            a["win_start"], a["win_end"] = buf("win_start", W, np.int32), buf("win_end", W, np.int32)
+        L = self._lib
+        _lib.check(L.amira_gmg_export_nodes(self._h, _ptr(a["node_key"]), _ptr(a["node_cov"]), _ptr(a["node_dir"]),
+                                            _ptr(a["node_comp"]), _ptr(a["node_reads_off"]), _ptr(a["node_reads"]),
+                                            _ptr(a["fw_off"]), _ptr(a["fw_edges"]), _ptr(a["bw_off"]), _ptr(a["bw_edges"])))
+        _lib.check(L.amira_gmg_export_edges(self._h, _ptr(a["edge_src"]), _ptr(a["edge_tgt"]), _ptr(a["edge_sd"]),
+                                            _ptr(a["edge_td"]), _ptr(a["edge_cov"])))
+        _lib.check(L.amira_gmg_export_reads(self._h, _ptr(a["win_off"]), _ptr(a["win_node"]), _ptr(a["win_dir"]),
+                                            _ptr(a.get("win_start")), _ptr(a.get("win_end")), _ptr(a["is_short"]),
+                                            _ptr(a["to_correct"])))
+        if not self.has_pos:
+            a["win_start"] = np.full(W, -1, np.int32)
+            a["win_end"] = np.full(W, -1, np.int32)
+        if n == 0:
+            for f in ("node_reads_off", "fw_off", "bw_off"):
+                a[f][:] = 0
+        if R == 0:
+            a["win_off"][:] = 0
+        return a

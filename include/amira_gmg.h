@@ -52,14 +52,15 @@ enum {
     AMIRA_PH_H2D = 0,        /* host -> device copy of the CSR input */
     AMIRA_PH_WINDOWS = 1,    /* per-read window counts + scan */
     AMIRA_PH_INSERT = 2,     /* k_insert_windows: enumerate, canonicalise, hash, node + edge tables */
-    AMIRA_PH_ORDER = 3,      /* first-seen ordering of nodes and edges, node/edge arrays */
+    AMIRA_PH_ORDER = 3,      /* first-seen ranks of nodes and edges (bitmap + prefix popcount) */
     AMIRA_PH_REMAP = 4,      /* per-window slot -> node index */
     AMIRA_PH_INCIDENCE = 5,  /* node -> reads CSR */
     AMIRA_PH_ADJACENCY = 6,  /* node -> forward/backward edge CSR */
     AMIRA_PH_COMPONENTS = 7, /* connected components */
     AMIRA_PH_FILTER = 8,     /* last filter / component removal */
     AMIRA_PH_EXCHANGE = 9,   /* multi-GPU all-to-all + merge */
-    AMIRA_PH_COUNT = 10
+    AMIRA_PH_EMIT = 10,      /* node / edge arrays in first-seen order + union-find */
+    AMIRA_PH_COUNT = 11
 };
 
 const char *amira_last_error(void);

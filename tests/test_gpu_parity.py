@@ -1,0 +1,112 @@
+"""GPU parity through the C ABI: amira_gmg_build / filter / exports vs the golden vectors from the
+unmodified upstream class and vs the C oracle on seeded synthetic inputs (bit-exact, all fields)."""
+import numpy as np
+import pytest
+
+from tests.helpers import EXPECTED, GOLDEN_KEYS, STAGE_ORDER, apply_stage, load_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dg():
+    from amira_b200.device_graph import DeviceGraph
+    g = DeviceGraph(0)
+    yield g
+    g.close()
+
+
+@pytest.mark.parametrize("key", GOLDEN_KEYS)
+def test_gpu_matches_upstream_golden(dg, key):
+    from oracle import gmg_oracle as O
+    exp = EXPECTED[key]
+    vocab, ids, off, ps, pe = load_input(exp["input"])
+    dg.build(ids, off, exp["k"], ps, pe)
+    for stage in STAGE_ORDER:
+        want = exp["stages"].get(stage)
+        if want is None:
+            break
+        if "raises" in want:
+            with pytest.raises(TypeError):
+                apply_stage(dg, stage)
+            break
+        apply_stage(dg, stage)
+        a = dg.arrays()
+        assert O.summary(a) == want["summary"], (key, stage)
+        got = O.digest_arrays(a)
+        assert got == want["digest"], (key, stage, [f for f in got if got[f] != want["digest"][f]])
+
+
+SYNTH = [("c2", 20000, 3, False), ("c2", 20000, 5, True), ("c3", 60000, 3, False), ("c3", 60000, 7, False),
+         ("c4", 50000, 3, False), ("c5", 40000, 5, False), ("c5", 5000, 15, False), ("c3", 3000, 1, False)]
+
+
+@pytest.mark.parametrize("cfg_name,n_reads,k,with_pos", SYNTH)
+def test_gpu_matches_c_oracle_on_synthetic(dg, cfg_name, n_reads, k, with_pos):
+    from amira_b200 import synth
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    cfg = synth.CONFIGS[cfg_name]
+    ids, off = synth.generate(cfg, 0, n_reads)
+    ps = pe = None
+    if with_pos:
+        ps, pe = synth.positions_for(off, 7)
+    ref = c_oracle.COracleGraph(ids, off, k, ps, pe)
+    dg.build(ids, off, k, ps, pe)
+    assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
+    if k == 1:
+        return
+    ref.remove_low_coverage_components(5)
+    dg.remove_low_coverage_components(5)
+    assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
+    ref.filter_graph(3, 1)
+    dg.filter_graph(3, 1)
+    assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
+    ref.filter_graph(4, 6)
+    dg.filter_graph(4, 6)
+    assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
+
+
+def test_gpu_edge_cases(dg):
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    # no reads at all, any k (upstream tests/test_gene_mer_graph.py:14-36)
+    for k in (0, 3):
+        dg.build(np.zeros(0, np.int32), np.zeros(1, np.int64), k)
+        assert O.summary(dg.arrays())["nodes"] == 0
+    # only empty / short reads
+    off = np.array([0, 0, 2, 2, 4, 4], np.int64)
+    ids = np.array([1, 2, -2, -1], np.int32)
+    dg.build(ids, off, 3)
+    a = dg.arrays()
+    assert a["is_short"].tolist() == [1, 1, 1, 1, 1] and len(a["node_cov"]) == 0
+    # ragged: empty reads between real ones, reads longer than a tile, a tile boundary inside a read
+    rng = np.random.default_rng(1)
+    lens = np.concatenate([[0, 0, 3000, 0, 1, 2, 3, 0, 1500], rng.integers(0, 40, 500), [0, 0]])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ids = (rng.integers(1, 50, off[-1]) * rng.choice([-1, 1], off[-1])).astype(np.int32)
+    for k in (1, 3, 5):
+        ref = c_oracle.COracleGraph(ids, off, k)
+        dg.build(ids, off, k)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], k
+    # palindromic even-k window -> AssertionError like upstream (construct_gene_mer.py:23-25)
+    with pytest.raises(AssertionError):
+        dg.build(np.array([5, -5, 7], np.int32), np.array([0, 3], np.int64), 2)
+    with pytest.raises(AssertionError):
+        dg.build(np.array([5, 6, 7], np.int32), np.array([0, 3], np.int64), 0)
+    # the handle survives an error
+    dg.build(np.array([5, 6, 7, 8], np.int32), np.array([0, 4], np.int64), 3)
+    assert dg.sizes()["nodes"] == 2
+
+
+def test_gpu_device_resident_input(dg):
+    import torch
+    from amira_b200 import synth
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    ids, off = synth.generate(synth.CONFIGS["c2"], 0, 10000)
+    d_ids = torch.from_numpy(ids).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    torch.cuda.synchronize()
+    dg.build(d_ids, d_off, 3, on_device=True)
+    assert O.diff_arrays(dg.arrays(), c_oracle.COracleGraph(ids, off, 3).arrays()) == []
