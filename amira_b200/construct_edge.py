@@ -9,7 +9,7 @@ from .construct_gene import hashlib_hash
 
 
 def extract_node_hashes(firstNode, secondNode):
-    return hash(firstNode), hash(secondNode)
+    return firstNode.__hash__(), secondNode.__hash__()
 
 
 def sort_node_hashes(firstNodeHash, secondNodeHash):
@@ -78,10 +78,10 @@ class Edge:
         return self.edgeCoverage
 
     def __eq__(self, otherEdge) -> bool:
-        mine = sorted((hash(self.sourceNode), hash(self.targetNode)))
-        theirs = sorted((hash(otherEdge.get_sourceNode()), hash(otherEdge.get_targetNode())))
+        mine = sorted((self.sourceNode.__hash__(), self.targetNode.__hash__()))
+        theirs = sorted((otherEdge.get_sourceNode().__hash__(), otherEdge.get_targetNode().__hash__()))
         return mine == theirs
 
     def __hash__(self):
-        return edge_key(hash(self.sourceNode), hash(self.targetNode), self.sourceNodeDirection,
+        return edge_key(self.sourceNode.__hash__(), self.targetNode.__hash__(), self.sourceNodeDirection,
                         self.targetNodeDirection)

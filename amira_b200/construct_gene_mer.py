@@ -15,8 +15,8 @@ def define_rc_geneMer(geneMer):
 
 
 def sort_geneMers(geneMer, rcGeneMer):
-    fwd = [hash(g) for g in geneMer]
-    rev = [hash(g) for g in rcGeneMer]
+    fwd = [g.__hash__() for g in geneMer]
+    rev = [g.__hash__() for g in rcGeneMer]
     assert fwd != rev, "Gene-mer and reverse complement gene-mer are identical"
     return fwd, rev, sorted((fwd, rev))
 
@@ -73,5 +73,5 @@ class GeneMer:
     def __hash__(self):
         """SHA-256 of the tuple of canonical signed gene hashes -- the node key (construct_gene_mer.py:94-97)"""
         if self._hash is None:
-            self._hash = hashlib_hash(tuple(hash(g) for g in self.canonicalGeneMer))
+            self._hash = hashlib_hash(tuple(g.__hash__() for g in self.canonicalGeneMer))
         return self._hash

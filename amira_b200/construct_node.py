@@ -15,7 +15,7 @@ class Node:
         self.geneMer = geneMer
         self.canonicalGeneMer = geneMer.get_canonical_geneMer()
         self.reverseGeneMer = geneMer.get_rc_geneMer()
-        self.geneMerHash = hash(geneMer)
+        self.geneMerHash = geneMer.__hash__()
         self.nodeCoverage = 0
         self.listOfReads = []
         self.forwardEdgeHashes = []
@@ -122,7 +122,7 @@ class Node:
             self._color = 2 if degree > 2 else 1
 
     def __eq__(self, otherNode):
-        return hash(self) == hash(otherNode) and self.nodeCoverage == otherNode.get_node_coverage()
+        return self.__hash__() == otherNode.__hash__() and self.nodeCoverage == otherNode.get_node_coverage()
 
     def __hash__(self):
         return self.geneMerHash

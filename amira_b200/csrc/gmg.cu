@@ -46,6 +46,8 @@ struct amira_gmg {
     DevBuf ntab, etab, bitmaps, cnt_node, cnt_edge;
     unsigned int ncap = 0, ecap = 0;
     int64_t hint_nodes = 0, hint_edges = 0;
+    int64_t filt_N = -1, filt_E = -1;  // node / edge counts before the last filter (keep flags are retained)
+    int64_t prev_G = 0, prev_nodes = 0, prev_und_edges = 0;  // sizes of the previous build on this handle
     // nodes (cur) and compaction targets (alt)
     DevBuf node_key, node_cov, node_dir, node_comp, reads_off, reads;
     DevBuf node_key2, node_cov2, node_dir2, node_comp2, reads_off2, reads2;
@@ -217,8 +219,16 @@ int do_build(amira_gmg *h) {
     unsigned int *bm_ea = bm_node + (n_words + 1), *bm_eb = bm_ea + (n_words + 1);
 
     // ---- hash tables: sized from hints or from the call count; retried larger on overflow
-    int64_t ncap = h->hint_nodes > 0 ? h->hint_nodes * 2 + 1024 : std::max<int64_t>(4096, G / 4);
-    int64_t ecap = h->hint_edges > 0 ? h->hint_edges * 2 + 1024 : std::max<int64_t>(4096, G / 4);
+    // Amira rebuilds the graph of (nearly) the same reads ~10-100x per sample: the previous build's
+    // unique counts, scaled by the call-count ratio, size the tables at ~50% load; a cold build uses
+    // G/4 slots.  Either way an overflow is detected on the device and retried larger.
+    int64_t ncap = std::max<int64_t>(4096, G / 4), ecap = std::max<int64_t>(4096, G / 4);
+    if (h->hint_nodes > 0) ncap = h->hint_nodes * 2 + 1024;
+    else if (h->prev_G > 0 && G <= 4 * h->prev_G)
+        ncap = (int64_t)((double)h->prev_nodes * ((double)G / (double)h->prev_G) * 2.0) + 4096;
+    if (h->hint_edges > 0) ecap = h->hint_edges * 2 + 1024;
+    else if (h->prev_G > 0 && G <= 4 * h->prev_G)
+        ecap = (int64_t)((double)h->prev_und_edges * ((double)G / (double)h->prev_G) * 2.0) + 4096;
     for (int attempt = 0;; ++attempt) {
         ncap = std::min<int64_t>(ncap, 0x7FFFFFF0ll);
         ecap = std::min<int64_t>(ecap, 0x7FFFFFF0ll);
@@ -288,6 +298,9 @@ int do_build(amira_gmg *h) {
     h->W = h->h_sizes[SZ_W];
     h->n_nodes = h->h_sizes[SZ_NODES];
     h->n_edges = h->h_sizes[SZ_EDGES];
+    h->prev_G = G;
+    h->prev_nodes = h->n_nodes;
+    h->prev_und_edges = (h->n_edges + 1) / 2 + 1;  // directed edges come in pairs, self-edges alone
     const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
 
     // ---- node / edge arrays in first-seen order, union-find on the way
@@ -373,6 +386,8 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
     const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
     const int k = h->k;
     cudaStream_t st = h->stream;
+    h->filt_N = N;
+    h->filt_E = E;
     if (N == 0) return AMIRA_OK;
     Phase ph(h, AMIRA_PH_FILTER);
     AMIRA_TRY(h->keep_n.reserve(sizeof(int) * 2 * (N + 2)));
@@ -589,6 +604,7 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
                     const int32_t *pos_start, const int32_t *pos_end, int input_on_device) {
     AMIRA_TRY(check_handle(h));
     h->built = false;
+    h->filt_N = h->filt_E = -1;
     reset_graph(h);
     for (int i = 0; i < AMIRA_PH_COUNT; ++i) h->ev_used[i] = false;
     if (R < 0 || k < 0 || (R > 0 && !read_off) || ((pos_start == nullptr) != (pos_end == nullptr))) {
@@ -771,6 +787,30 @@ int amira_gmg_remove_low_coverage_components(amira_gmg *h, uint32_t min_componen
 int amira_gmg_filter(amira_gmg *h, uint32_t min_node_cov, uint32_t min_edge_cov) {
     AMIRA_TRY(check_handle(h));
     return h->last_status = do_filter(h, 0, min_node_cov, min_edge_cov);
+}
+
+int amira_gmg_filter_mask_sizes(amira_gmg *h, int64_t *n_nodes_before, int64_t *n_edges_before) {
+    AMIRA_TRY(check_handle(h));
+    if (!h->built || h->filt_N < 0) {
+        set_error("no filter has run on this graph");
+        return AMIRA_E_STATE;
+    }
+    if (n_nodes_before) *n_nodes_before = h->filt_N;
+    if (n_edges_before) *n_edges_before = h->filt_E;
+    return AMIRA_OK;
+}
+
+int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edge_keep) {
+    AMIRA_TRY(check_handle(h));
+    if (!h->built || h->filt_N < 0) {
+        set_error("no filter has run on this graph");
+        return AMIRA_E_STATE;
+    }
+    if (h->filt_N == 0) return AMIRA_OK;
+    AMIRA_TRY(d2h(h, node_keep, h->keep_n.p, sizeof(int) * h->filt_N));
+    AMIRA_TRY(d2h(h, edge_keep, h->keep_e.p, sizeof(int) * h->filt_E));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
 }
 
 int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, double *red_add_per_s, double *cas_per_s) {

@@ -471,7 +471,11 @@ __global__ void k_cc_number(const int32_t *__restrict__ parent, const int *__res
 __global__ void k_component_max(const uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ comp,
                                 int64_t n_nodes, uint32_t *__restrict__ comp_max) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) atomicMax(&comp_max[comp[i]], node_cov[i]);
+    if (i < n_nodes) {
+        // one giant component is the common case: read first, the maximum only ever grows
+        const uint32_t c = comp[i], v = node_cov[i];
+        if (v > ((volatile uint32_t *)comp_max)[c]) atomicMax(&comp_max[c], v);
+    }
 }
 
 // keep flags: mode 0 = coverage >= thr (filter_graph), mode 1 = component max >= thr

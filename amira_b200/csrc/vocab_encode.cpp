@@ -32,7 +32,8 @@ extern "C" int amira_vocab_encode(const char *tokens_utf8, const int64_t *tok_of
         const size_t len = (size_t)(tok_off[t + 1] - tok_off[t]);
         auto fail = [&](int code, const char *what) {
             if (bad_token) *bad_token = t;
-            amira::set_error("%s%.*s", what, (int)len, s);
+            if (code == AMIRA_E_BLANK_GENE) amira::set_error("%s", what);
+            else amira::set_error("%s%.*s", what, (int)len, s);
             return code;
         };
         bool blank = true;

@@ -74,6 +74,14 @@ class DeviceGraph:
     def remove_low_coverage_components(self, min_component_cov: int):
         _lib.check(self._lib.amira_gmg_remove_low_coverage_components(self._h, int(min_component_cov)))
 
+    def filter_masks(self):
+        """keep flags of the last filter / component removal, indexed by the pre-filter node / edge order"""
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self._lib.amira_gmg_filter_mask_sizes(self._h, C.byref(a), C.byref(b)))
+        nk, ek = np.ones(a.value, np.int32), np.ones(b.value, np.int32)
+        _lib.check(self._lib.amira_gmg_export_filter_masks(self._h, _ptr(nk), _ptr(ek)))
+        return nk.astype(bool), ek.astype(bool)
+
     def sizes(self) -> dict:
         v = [C.c_int64() for _ in range(7)]
         _lib.check(self._lib.amira_gmg_sizes(self._h, *[C.byref(x) for x in v]))
@@ -97,6 +105,13 @@ class DeviceGraph:
         a, b = C.c_double(), C.c_double()
         _lib.check(self._lib.amira_gmg_atomic_peak(self._h, int(table_bytes), int(n_ops), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def arrays_reads_only(self) -> dict:
+        """only the per-window node indices (what changes in the per-read lists after a removal)"""
+        s = self.sizes()
+        a = {"win_node": np.empty(s["windows"], np.int32)}
+        _lib.check(self._lib.amira_gmg_export_reads(self._h, None, _ptr(a["win_node"]), None, None, None, None, None))
+        return a
 
     def arrays(self, out=None) -> dict:
         """export every graph array to host memory (numpy); `out` may supply preallocated buffers"""

@@ -125,6 +125,12 @@ int amira_gmg_export_reads(amira_gmg *h, int64_t *win_off, int32_t *node_idx, in
 int amira_gmg_remove_low_coverage_components(amira_gmg *h, uint32_t min_component_cov);
 int amira_gmg_filter(amira_gmg *h, uint32_t min_node_cov, uint32_t min_edge_cov);
 
+/* Which nodes / edges the LAST filter or component removal kept: keep flags (1 = kept) indexed by the
+ * node / edge order BEFORE that call.  Lets a host mirror delete the same objects instead of
+ * re-creating the survivors.  Sizes via amira_gmg_filter_mask_sizes. */
+int amira_gmg_filter_mask_sizes(amira_gmg *h, int64_t *n_nodes_before, int64_t *n_edges_before);
+int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edge_keep);
+
 /* Multi-GPU (one process per GPU): reads are sharded contiguously over ranks, canonical gene-mers
  * are owned by hash range, partial tables are routed with an NCCL all-to-all.  nccl_unique_id is
  * the 128-byte ncclUniqueId of rank 0.  After comm_init, amira_gmg_build takes this rank's shard and
