@@ -254,6 +254,7 @@ int do_build(amira_gmg *h) {
                 P.status = h->d_status.as<int>();
                 P.read_base = h->first_read_global;
                 const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sm * h->insert_ctas_per_sm);
+                Phase phk(h, AMIRA_PH_INSERT_KERNEL);
                 LAUNCH(h, k_insert_windows, grid, INS_THREADS, P);
             }
         }

@@ -106,6 +106,19 @@ class DeviceGraph:
         _lib.check(self._lib.amira_gmg_atomic_peak(self._h, int(table_bytes), int(n_ops), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    # ---- multi-GPU: one process per GPU, contiguous read shards in rank order ----------------------
+    def nccl_unique_id(self) -> np.ndarray:
+        """128-byte ncclUniqueId (rank 0 creates it, every rank passes it to comm_init)"""
+        uid = np.zeros(128, np.uint8)
+        _lib.check(self._lib.amira_gmg_nccl_unique_id(_ptr(uid)))
+        return uid
+
+    def comm_init(self, unique_id, rank: int, world: int):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == 128
+        _lib.check(self._lib.amira_gmg_comm_init(self._h, _ptr(uid), int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
     def arrays_reads_only(self) -> dict:
         """only the per-window node indices (what changes in the per-read lists after a removal)"""
         s = self.sizes()
@@ -147,7 +160,7 @@ class DeviceGraph:
         _lib.check(L.amira_gmg_export_reads(self._h, _ptr(a["win_off"]), _ptr(a["win_node"]), _ptr(a["win_dir"]),
                                             _ptr(a.get("win_start")), _ptr(a.get("win_end")), _ptr(a["is_short"]),
                                             _ptr(a["to_correct"])))
-        if not self.has_pos:
+        if not self.has_pos and out is None:
             a["win_start"] = np.full(W, -1, np.int32)
             a["win_end"] = np.full(W, -1, np.int32)
         if n == 0:

@@ -60,7 +60,8 @@ enum {
     AMIRA_PH_FILTER = 8,     /* last filter / component removal */
     AMIRA_PH_EXCHANGE = 9,   /* multi-GPU all-to-all + merge */
     AMIRA_PH_EMIT = 10,      /* node / edge arrays in first-seen order + union-find */
-    AMIRA_PH_COUNT = 11
+    AMIRA_PH_INSERT_KERNEL = 11, /* k_insert_windows alone (inside AMIRA_PH_INSERT, which also clears the tables) */
+    AMIRA_PH_COUNT = 12
 };
 
 const char *amira_last_error(void);
