@@ -103,6 +103,20 @@ struct EdgeSlot {
 };
 static_assert(sizeof(EdgeSlot) == 32, "EdgeSlot must be 32 bytes");
 
+// ---- multi-GPU plumbing (comm.cu) ----------------------------------------------------------------
+struct Comm;
+int comm_unique_id(void *out_128_bytes);
+int comm_create(Comm **out, const void *unique_id, int rank, int world);
+void comm_destroy(Comm *c);
+int comm_rank(const Comm *c);
+int comm_world(const Comm *c);
+int comm_allgather(Comm *c, const void *d_send, void *d_recv, size_t bytes_per_rank, cudaStream_t st);
+int comm_allreduce_max_i32(Comm *c, int *d_buf, int n, cudaStream_t st);
+int comm_alltoallv(Comm *c, const void *d_send, const int64_t *send_off, void *d_recv, const int64_t *recv_off,
+                   size_t elem_bytes, cudaStream_t st);
+int comm_allgatherv(Comm *c, const void *d_send, int64_t n_send, void *d_recv, const int64_t *recv_off,
+                    size_t elem_bytes, cudaStream_t st);
+
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33;
     x *= 0xff51afd7ed558ccdULL;

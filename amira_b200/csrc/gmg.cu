@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "gmg_kernels.cuh"
+#include "sharded.cuh"
 
 namespace amira {
 
@@ -74,10 +75,13 @@ struct amira_gmg {
     int64_t launches = 0;      // hand-written kernels launched
     int64_t lib_launches = 0;  // CUB / memset / memcpy calls
 
-    // multi-GPU
-    void *comm = nullptr;
+    // multi-GPU (sharded.cuh): exchange scratch, local coverage per global node
+    Comm *comm = nullptr;
     int rank = 0, world = 1;
     int64_t first_read_global = 0, first_call_global = 0;
+    DevBuf x_cnt, x_skey, x_smeta, x_rkey, x_rmeta, x_rkey2, x_rmeta2, x_mkey, x_mmeta, x_gkey, x_gmeta, x_tab,
+        x_sortk, x_sortk2, x_sorti, x_sorti2, x_sedge, x_redge, x_medge, x_gedge, x_etab, x_fan, cov_local;
+    long long *h_cnt = nullptr;  // pinned, world*world + 4
 };
 
 namespace {
@@ -137,6 +141,8 @@ void reset_graph(amira_gmg *h) {
     h->n_nodes = h->n_edges = h->W = h->n_inc = h->n_short = h->n_fw = h->n_bw = h->n_comps = 0;
     h->sizes_dirty = false;
 }
+
+int sharded_merge(amira_gmg *h);
 
 // node -> forward/backward edge CSR from the current edge arrays
 int build_adjacency(amira_gmg *h) {
@@ -258,7 +264,9 @@ int do_build(amira_gmg *h) {
                 LAUNCH(h, k_insert_windows, grid, INS_THREADS, P);
             }
         }
-        {
+        if (h->world > 1) {
+            LAUNCH(h, k_set_w, 1, 32, h->win_off.as<int64_t>(), R, h->d_sizes.as<long long>());
+        } else {
             Phase ph(h, AMIRA_PH_ORDER);
             AMIRA_CUDA(cudaMemsetAsync(h->bitmaps.p, 0, sizeof(unsigned int) * 3 * (n_words + 1), st));
             const unsigned int tmax = std::max(h->ncap, h->ecap);
@@ -290,6 +298,12 @@ int do_build(amira_gmg *h) {
         AMIRA_CUDA(cudaStreamSynchronize(st));
     }
     h->n_short = h->h_sizes[SZ_SHORT];
+    if (h->world > 1) {
+        // every rank must leave the build together: agree on the error status before any exchange
+        AMIRA_TRY(comm_allreduce_max_i32(h->comm, h->d_status.as<int>(), ST_COUNT, st));
+        AMIRA_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, st));
+        AMIRA_CUDA(cudaStreamSynchronize(st));
+    }
     if (h->h_status[ST_ERR]) {
         const int e = h->h_status[ST_ERR];
         if (e == AMIRA_E_PALINDROME) set_error("Gene-mer and reverse complement gene-mer are identical");
@@ -297,15 +311,19 @@ int do_build(amira_gmg *h) {
         return e;
     }
     h->W = h->h_sizes[SZ_W];
-    h->n_nodes = h->h_sizes[SZ_NODES];
-    h->n_edges = h->h_sizes[SZ_EDGES];
     h->prev_G = G;
-    h->prev_nodes = h->n_nodes;
-    h->prev_und_edges = (h->n_edges + 1) / 2 + 1;  // directed edges come in pairs, self-edges alone
+    if (h->world > 1) {
+        AMIRA_TRY(sharded_merge(h));
+    } else {
+        h->n_nodes = h->h_sizes[SZ_NODES];
+        h->n_edges = h->h_sizes[SZ_EDGES];
+        h->prev_nodes = h->n_nodes;
+        h->prev_und_edges = (h->n_edges + 1) / 2 + 1;  // directed edges come in pairs, self-edges alone
+    }
     const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
 
     // ---- node / edge arrays in first-seen order, union-find on the way
-    {
+    if (h->world == 1) {
         Phase ph(h, AMIRA_PH_EMIT);
         AMIRA_TRY(h->node_key.reserve(sizeof(int32_t) * std::max<int64_t>(1, N * k)));
         AMIRA_TRY(h->node_cov.reserve(sizeof(uint32_t) * (N + 1)));
@@ -359,7 +377,11 @@ int do_build(amira_gmg *h) {
                                                   h->reads.as<int32_t>(), h->d_nsel.as<long long>(), W, st);
             }));
         }
-        LAUNCH(h, k_incidence_counts, grid_for(N + 1, 256), 256, h->node_cov.as<uint32_t>(), h->dups.as<uint32_t>(), N,
+        if (W > 0 && h->first_read_global != 0)  // Node.listOfReads holds global read indices
+            LAUNCH(h, k_add_i32, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->reads.as<int32_t>(), (long long)W,
+                   (int32_t)h->first_read_global);
+        LAUNCH(h, k_incidence_counts, grid_for(N + 1, 256), 256,
+               h->world > 1 ? h->cov_local.as<uint32_t>() : h->node_cov.as<uint32_t>(), h->dups.as<uint32_t>(), N,
                h->reads_off.as<int64_t>());
         AMIRA_TRY(exclusive_sum_inplace(h, h->reads_off.as<int64_t>(), N + 1));
     }
@@ -474,6 +496,224 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
     return AMIRA_OK;
 }
 
+// ---- multi-GPU: merge the local tables of all ranks into the global node / edge arrays ----------
+// (see sharded.cuh for the scheme)
+int sort_by_ord(amira_gmg *h, long long n) {
+    // x_sortk / x_sorti -> x_sortk2 / x_sorti2; positions use P_BITS bits plus two flag bits
+    if (n <= 0) return AMIRA_OK;
+    return cub_call(h, [&](void *t, size_t &b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, h->x_sortk.as<unsigned long long>(),
+                                               h->x_sortk2.as<unsigned long long>(), h->x_sorti.as<unsigned int>(),
+                                               h->x_sorti2.as<unsigned int>(), n, 0, P_BITS + 3, h->stream);
+    });
+}
+
+// counts[world] on the device -> the world x world matrix on the host; fills send_off / recv_off
+int exchange_counts(amira_gmg *h, std::vector<int64_t> &send_off, std::vector<int64_t> &recv_off) {
+    const int world = h->world, me = h->rank;
+    unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
+    unsigned long long *d_mat = d_cnt + 2 * MAX_WORLD;
+    AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_mat, sizeof(unsigned long long) * world, h->stream));
+    AMIRA_CUDA(cudaMemcpyAsync(h->h_cnt, d_mat, sizeof(unsigned long long) * world * world, cudaMemcpyDeviceToHost,
+                               h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    send_off.assign(world + 1, 0);
+    recv_off.assign(world + 1, 0);
+    for (int p = 0; p < world; ++p) {
+        send_off[p + 1] = send_off[p] + h->h_cnt[(int64_t)me * world + p];
+        recv_off[p + 1] = recv_off[p] + h->h_cnt[(int64_t)p * world + me];
+    }
+    // destination offsets for the scatter pass, cursors back to zero
+    long long *d_off = (long long *)(d_cnt + MAX_WORLD);
+    AMIRA_CUDA(cudaMemcpyAsync(d_off, send_off.data(), sizeof(long long) * world, cudaMemcpyHostToDevice, h->stream));
+    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));  // send_off lives on this stack frame's caller
+    return AMIRA_OK;
+}
+
+// one counter per rank -> offsets of the all-gather-v
+int gather_counts(amira_gmg *h, std::vector<int64_t> &off) {
+    const int world = h->world;
+    unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
+    unsigned long long *d_mat = d_cnt + 2 * MAX_WORLD;
+    AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_mat, sizeof(unsigned long long), h->stream));
+    AMIRA_CUDA(cudaMemcpyAsync(h->h_cnt, d_mat, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, h->stream));
+    AMIRA_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    off.assign(world + 1, 0);
+    for (int p = 0; p < world; ++p) off[p + 1] = off[p] + h->h_cnt[p];
+    return AMIRA_OK;
+}
+
+int sharded_merge(amira_gmg *h) {
+    Phase ph(h, AMIRA_PH_EXCHANGE);
+    const int world = h->world, k = h->k;
+    cudaStream_t st = h->stream;
+    const int tgrid_n = std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16);
+    const int tgrid_e = std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16);
+    const long long call_base = h->first_call_global;
+    AMIRA_TRY(h->x_cnt.reserve(sizeof(unsigned long long) * (2 * MAX_WORLD + (size_t)world * world + 8)));
+    unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
+    const long long *d_off = (const long long *)(d_cnt + MAX_WORLD);
+    std::vector<int64_t> send_off, recv_off, g_off;
+    const size_t key_bytes = sizeof(int32_t) * (size_t)k;
+
+    // ---- nodes: route one record per locally-unique gene-mer to its owner
+    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, st));
+    LAUNCH(h, k_node_route<false>, tgrid_n, 256, h->ntab.as<NodeSlot>(), h->ncap, h->ids, k, world, call_base, d_cnt,
+           nullptr, nullptr, nullptr);
+    AMIRA_TRY(exchange_counts(h, send_off, recv_off));
+    const int64_t Nl = send_off[world], Nr = recv_off[world];
+    AMIRA_TRY(h->x_skey.reserve(key_bytes * std::max<int64_t>(Nl, 1)));
+    AMIRA_TRY(h->x_smeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nl, 1)));
+    AMIRA_TRY(h->x_rkey.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
+    AMIRA_TRY(h->x_rmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
+    AMIRA_TRY(h->x_rkey2.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
+    AMIRA_TRY(h->x_rmeta2.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
+    LAUNCH(h, k_node_route<true>, tgrid_n, 256, h->ntab.as<NodeSlot>(), h->ncap, h->ids, k, world, call_base, d_cnt, d_off,
+           h->x_skey.as<int32_t>(), h->x_smeta.as<NodeRec>());
+    AMIRA_TRY(comm_alltoallv(h->comm, h->x_skey.p, send_off.data(), h->x_rkey.p, recv_off.data(), key_bytes, st));
+    AMIRA_TRY(comm_alltoallv(h->comm, h->x_smeta.p, send_off.data(), h->x_rmeta.p, recv_off.data(), sizeof(NodeRec), st));
+
+    // ---- owner merge: records in first-position order into a table (sum of counts, earliest record)
+    const int64_t sort_cap = std::max<int64_t>(Nr, 1);
+    AMIRA_TRY(h->x_sortk.reserve(sizeof(unsigned long long) * sort_cap));
+    AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * sort_cap));
+    AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * sort_cap));
+    AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * sort_cap));
+    int64_t mcap = std::min<int64_t>(2 * Nr + 1024, 0x7FFFFFF0ll);
+    AMIRA_TRY(h->x_tab.reserve(sizeof(NodeSlot) * mcap));
+    AMIRA_TRY(h->x_mkey.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
+    AMIRA_TRY(h->x_mmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
+    AMIRA_CUDA(cudaMemsetAsync(h->x_tab.p, 0xFF, sizeof(NodeSlot) * mcap, st));
+    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+    BuildParams P;
+    memset(&P, 0, sizeof(P));
+    P.k = k;
+    P.status = h->d_status.as<int>();
+    if (Nr > 0) {
+        LAUNCH(h, k_rec_ord_keys, grid_for(Nr, 256), 256, h->x_rmeta.as<NodeRec>(), (long long)Nr,
+               h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
+        AMIRA_TRY(sort_by_ord(h, Nr));
+        LAUNCH(h, k_gather_node_recs, grid_for(Nr, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_rkey.as<int32_t>(),
+               h->x_rmeta.as<NodeRec>(), k, (long long)Nr, h->x_rkey2.as<int32_t>(), h->x_rmeta2.as<NodeRec>());
+        P.ids = h->x_rkey2.as<int32_t>();
+        P.ntab = h->x_tab.as<NodeSlot>();
+        P.ncap = (unsigned int)mcap;
+        LAUNCH(h, k_insert_records, grid_for(Nr, 256), 256, P, (long long)Nr, h->x_rmeta2.as<NodeRec>());
+        LAUNCH(h, k_pack_merged_nodes, std::min<int>(grid_for(mcap, 256), h->n_sm * 16), 256, h->x_tab.as<NodeSlot>(),
+               (unsigned int)mcap, h->x_rkey2.as<int32_t>(), h->x_rmeta2.as<NodeRec>(), k, d_cnt, h->x_mkey.as<int32_t>(),
+               h->x_mmeta.as<NodeRec>());
+    }
+    AMIRA_TRY(gather_counts(h, g_off));
+    const int64_t Nm = g_off[h->rank + 1] - g_off[h->rank], Ng = g_off[world];
+    if (Ng >= 0x7FFFFFF0ll) {
+        set_error("too many nodes for int32 node indices");
+        return AMIRA_E_ARG;
+    }
+    AMIRA_TRY(h->x_gkey.reserve(key_bytes * std::max<int64_t>(Ng, 1)));
+    AMIRA_TRY(h->x_gmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Ng, 1)));
+    AMIRA_TRY(comm_allgatherv(h->comm, h->x_mkey.p, Nm, h->x_gkey.p, g_off.data(), key_bytes, st));
+    AMIRA_TRY(comm_allgatherv(h->comm, h->x_mmeta.p, Nm, h->x_gmeta.p, g_off.data(), sizeof(NodeRec), st));
+
+    // ---- global node arrays in upstream's insertion order (= first global position)
+    AMIRA_TRY(h->node_key.reserve(key_bytes * std::max<int64_t>(1, Ng)));
+    AMIRA_TRY(h->node_cov.reserve(sizeof(uint32_t) * (Ng + 1)));
+    AMIRA_TRY(h->node_dir.reserve(Ng + 1));
+    AMIRA_TRY(h->node_comp.reserve(sizeof(uint32_t) * (Ng + 1)));
+    AMIRA_TRY(h->parent.reserve(sizeof(int32_t) * (Ng + 1)));
+    AMIRA_TRY(h->is_root.reserve(sizeof(int) * (Ng + 2)));
+    AMIRA_TRY(h->cov_local.reserve(sizeof(uint32_t) * (Ng + 1)));
+    AMIRA_CUDA(cudaMemsetAsync(h->cov_local.p, 0, sizeof(uint32_t) * (Ng + 1), st));
+    if (Ng > 0) {
+        AMIRA_TRY(h->x_sortk.reserve(sizeof(unsigned long long) * Ng));
+        AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * Ng));
+        AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * Ng));
+        AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * Ng));
+        LAUNCH(h, k_rec_ord_keys, grid_for(Ng, 256), 256, h->x_gmeta.as<NodeRec>(), (long long)Ng,
+               h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
+        AMIRA_TRY(sort_by_ord(h, Ng));
+        LAUNCH(h, k_finalize_nodes, grid_for(Ng, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_gkey.as<int32_t>(),
+               h->x_gmeta.as<NodeRec>(), k, (long long)Ng, h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
+               h->node_dir.as<int8_t>(), h->parent.as<int32_t>());
+        // lookup table over the global nodes; local slots -> global node indices
+        mcap = std::min<int64_t>(2 * Ng + 1024, 0x7FFFFFF0ll);
+        AMIRA_TRY(h->x_tab.reserve(sizeof(NodeSlot) * mcap));
+        AMIRA_CUDA(cudaMemsetAsync(h->x_tab.p, 0xFF, sizeof(NodeSlot) * mcap, st));
+        P.ids = h->node_key.as<int32_t>();
+        P.ntab = h->x_tab.as<NodeSlot>();
+        P.ncap = (unsigned int)mcap;
+        LAUNCH(h, k_insert_records, grid_for(Ng, 256), 256, P, (long long)Ng, nullptr);
+        LAUNCH(h, k_local_to_global, tgrid_n, 256, h->ntab.as<NodeSlot>(), h->ncap, h->x_skey.as<int32_t>(), P,
+               h->cov_local.as<uint32_t>());
+    }
+
+    // ---- edges: one record per locally-unique undirected adjacency, keyed on global node indices
+    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, st));
+    LAUNCH(h, k_edge_route<false>, tgrid_e, 256, h->etab.as<EdgeSlot>(), h->ecap, h->ntab.as<NodeSlot>(), world, call_base,
+           d_cnt, nullptr, nullptr);
+    AMIRA_TRY(exchange_counts(h, send_off, recv_off));
+    const int64_t El = send_off[world], Er = recv_off[world];
+    AMIRA_TRY(h->x_sedge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(El, 1)));
+    AMIRA_TRY(h->x_redge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Er, 1)));
+    AMIRA_TRY(h->x_medge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Er, 1)));
+    LAUNCH(h, k_edge_route<true>, tgrid_e, 256, h->etab.as<EdgeSlot>(), h->ecap, h->ntab.as<NodeSlot>(), world, call_base,
+           d_cnt, d_off, h->x_sedge.as<EdgeSlot>());
+    AMIRA_TRY(comm_alltoallv(h->comm, h->x_sedge.p, send_off.data(), h->x_redge.p, recv_off.data(), sizeof(EdgeSlot), st));
+    const int64_t mecap = std::min<int64_t>(2 * Er + 1024, 0x7FFFFFF0ll);
+    AMIRA_TRY(h->x_etab.reserve(sizeof(EdgeSlot) * mecap));
+    AMIRA_CUDA(cudaMemsetAsync(h->x_etab.p, 0xFF, sizeof(EdgeSlot) * mecap, st));
+    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+    if (Er > 0) {
+        LAUNCH(h, k_merge_edges, grid_for(Er, 256), 256, h->x_redge.as<EdgeSlot>(), (long long)Er, h->x_etab.as<EdgeSlot>(),
+               (unsigned int)mecap, h->d_status.as<int>());
+        LAUNCH(h, k_pack_merged_edges, std::min<int>(grid_for(mecap, 256), h->n_sm * 16), 256, h->x_etab.as<EdgeSlot>(),
+               (unsigned int)mecap, d_cnt, h->x_medge.as<EdgeSlot>());
+    }
+    AMIRA_TRY(gather_counts(h, g_off));
+    const int64_t Em = g_off[h->rank + 1] - g_off[h->rank], Eg = g_off[world];
+    AMIRA_TRY(h->x_gedge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Eg, 1)));
+    AMIRA_TRY(comm_allgatherv(h->comm, h->x_medge.p, Em, h->x_gedge.p, g_off.data(), sizeof(EdgeSlot), st));
+    int64_t E_dir = 0;
+    AMIRA_TRY(h->x_fan.reserve(sizeof(int) * (Eg + 2)));
+    if (Eg > 0) {
+        AMIRA_TRY(h->x_sortk.reserve(sizeof(unsigned long long) * Eg));
+        AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * Eg));
+        AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * Eg));
+        AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * Eg));
+        LAUNCH(h, k_edge_ord_keys, grid_for(Eg, 256), 256, h->x_gedge.as<EdgeSlot>(), (long long)Eg,
+               h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
+        AMIRA_TRY(sort_by_ord(h, Eg));
+        LAUNCH(h, k_edge_fanout, grid_for(Eg + 1, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_gedge.as<EdgeSlot>(),
+               (long long)Eg, h->x_fan.as<int>());
+        AMIRA_TRY(exclusive_sum_inplace(h, h->x_fan.as<int>(), Eg + 1));
+        int e_dir32 = 0;
+        AMIRA_CUDA(cudaMemcpyAsync(&e_dir32, h->x_fan.as<int>() + Eg, sizeof(int), cudaMemcpyDeviceToHost, st));
+        AMIRA_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, st));
+        AMIRA_CUDA(cudaStreamSynchronize(st));
+        E_dir = e_dir32;
+    }
+    if (h->h_status[ST_ERR] || h->h_status[ST_OVERFLOW_N] || h->h_status[ST_OVERFLOW_E]) {
+        set_error("internal error while merging the sharded tables (status %d/%d/%d)", h->h_status[ST_ERR],
+                  h->h_status[ST_OVERFLOW_N], h->h_status[ST_OVERFLOW_E]);
+        return AMIRA_E_STATE;
+    }
+    AMIRA_TRY(h->e_src.reserve(sizeof(int32_t) * (E_dir + 1)));
+    AMIRA_TRY(h->e_tgt.reserve(sizeof(int32_t) * (E_dir + 1)));
+    AMIRA_TRY(h->e_sd.reserve(E_dir + 1));
+    AMIRA_TRY(h->e_td.reserve(E_dir + 1));
+    AMIRA_TRY(h->e_cov.reserve(sizeof(uint32_t) * (E_dir + 1)));
+    if (Eg > 0)
+        LAUNCH(h, k_emit_edges_sorted, grid_for(Eg, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_gedge.as<EdgeSlot>(),
+               h->x_fan.as<int>(), (long long)Eg, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
+               h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->parent.as<int32_t>());
+    h->n_nodes = Ng;
+    h->n_edges = E_dir;
+    h->prev_nodes = Nl;
+    h->prev_und_edges = El + 1;
+    return AMIRA_OK;
+}
+
 __global__ void k_sub_offset(const int64_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] - in[0];
@@ -559,8 +799,13 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
                       &h->adj_keys, &h->adj_keys2, &h->adj_vals, &h->sort_keys, &h->sort_vals, &h->flags, &h->dups,
                       &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,
-                      &h->d_nsel};
+                      &h->d_nsel, &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rkey2, &h->x_rmeta2,
+                      &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_sortk, &h->x_sortk2, &h->x_sorti,
+                      &h->x_sorti2, &h->x_sedge, &h->x_redge, &h->x_medge, &h->x_gedge, &h->x_etab, &h->x_fan,
+                      &h->cov_local};
     for (DevBuf *b : bufs) b->release();
+    if (h->comm) comm_destroy(h->comm);
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_sizes) cudaFreeHost(h->h_sizes);
     for (int i = 0; i < AMIRA_PH_COUNT; ++i)
@@ -620,7 +865,7 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
     h->k = k;
     h->has_pos = pos_start != nullptr;
     h->G = 0;
-    if (R == 0) {  // GeneMerGraph({}, k): empty graph for any k (tests/test_gene_mer_graph.py:14-36)
+    if (R == 0 && h->world == 1) {  // GeneMerGraph({}, k): empty graph for any k (tests/test_gene_mer_graph.py:14-36)
         h->built = true;
         return h->last_status = AMIRA_OK;
     }
@@ -635,10 +880,12 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
     cudaStream_t st = h->stream;
     int64_t G = 0;
     if (input_on_device) {
-        AMIRA_CUDA(cudaMemcpyAsync(&G, read_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        AMIRA_CUDA(cudaStreamSynchronize(st));
+        if (R > 0) {
+            AMIRA_CUDA(cudaMemcpyAsync(&G, read_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            AMIRA_CUDA(cudaStreamSynchronize(st));
+        }
     } else {
-        G = read_off[R];
+        G = R > 0 ? read_off[R] : 0;
     }
     if (G < 0 || G >= (1ll << (P_BITS - 1)) || (G > 0 && !signed_ids)) {
         set_error("bad call count %lld", (long long)G);
@@ -655,7 +902,8 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
         AMIRA_TRY(h->d_ids.reserve(sizeof(int32_t) * std::max<int64_t>(G, 1) + 16));
         AMIRA_TRY(h->d_off.reserve(sizeof(int64_t) * (R + 1)));
         if (G > 0) AMIRA_CUDA(cudaMemcpyAsync(h->d_ids.p, signed_ids, sizeof(int32_t) * G, cudaMemcpyHostToDevice, st));
-        AMIRA_CUDA(cudaMemcpyAsync(h->d_off.p, read_off, sizeof(int64_t) * (R + 1), cudaMemcpyHostToDevice, st));
+        if (read_off) AMIRA_CUDA(cudaMemcpyAsync(h->d_off.p, read_off, sizeof(int64_t) * (R + 1), cudaMemcpyHostToDevice, st));
+        else AMIRA_CUDA(cudaMemsetAsync(h->d_off.p, 0, sizeof(int64_t) * (R + 1), st));
         h->ids = h->d_ids.as<int32_t>();
         h->off = h->d_off.as<int64_t>();
         h->ps = h->pe = nullptr;
@@ -670,6 +918,35 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
             h->pe = h->d_pe.as<int32_t>();
         }
         h->lib_launches += 2;
+    }
+    h->first_read_global = h->first_call_global = 0;
+    if (h->world > 1) {
+        // contiguous shards in rank order: this rank's first global read / call index
+        AMIRA_TRY(h->x_cnt.reserve(sizeof(unsigned long long) * (2 * MAX_WORLD + (size_t)h->world * h->world + 8)));
+        long long mine[2] = {(long long)R, (long long)G};
+        unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
+        AMIRA_CUDA(cudaMemcpyAsync(d_cnt, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+        AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_cnt + 2 * MAX_WORLD, sizeof(mine), st));
+        AMIRA_CUDA(cudaMemcpyAsync(h->h_cnt, d_cnt + 2 * MAX_WORLD, sizeof(mine) * h->world, cudaMemcpyDeviceToHost, st));
+        AMIRA_CUDA(cudaStreamSynchronize(st));
+        long long r_all = 0, g_all = 0;
+        for (int p = 0; p < h->world; ++p) {
+            if (p == h->rank) {
+                h->first_read_global = r_all;
+                h->first_call_global = g_all;
+            }
+            r_all += h->h_cnt[2 * p];
+            g_all += h->h_cnt[2 * p + 1];
+        }
+        if (r_all >= 0x7FFFFFF0ll || g_all >= (1ll << (P_BITS - 1))) {
+            set_error("global read set too large (%lld reads, %lld calls)", r_all, g_all);
+            return h->last_status = AMIRA_E_ARG;
+        }
+        if (!h->off) {  // an empty shard still needs a valid offsets array
+            AMIRA_TRY(h->d_off.reserve(sizeof(int64_t) * 2));
+            AMIRA_CUDA(cudaMemsetAsync(h->d_off.p, 0, sizeof(int64_t) * 2, st));
+            h->off = h->d_off.as<int64_t>();
+        }
     }
     int rc = do_build(h);
     h->last_status = rc;
@@ -711,7 +988,7 @@ int amira_gmg_export_nodes(amira_gmg *h, int32_t *key, uint32_t *cov, int8_t *fi
     }
     AMIRA_TRY(finish_sizes(h));
     const int64_t N = h->n_nodes;
-    if (N == 0 || h->R == 0) {
+    if (N == 0) {
         if (reads_off) reads_off[0] = 0;
         if (fw_off) fw_off[0] = 0;
         if (bw_off) bw_off[0] = 0;
@@ -811,6 +1088,26 @@ int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edg
     AMIRA_TRY(d2h(h, node_keep, h->keep_n.p, sizeof(int) * h->filt_N));
     AMIRA_TRY(d2h(h, edge_keep, h->keep_e.p, sizeof(int) * h->filt_E));
     AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
+}
+
+int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int world) {
+    AMIRA_TRY(check_handle(h));
+    if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world || !nccl_unique_id) {
+        set_error("bad arguments to amira_gmg_comm_init (world must be 1..%d)", MAX_WORLD);
+        return AMIRA_E_ARG;
+    }
+    if (h->comm) {
+        comm_destroy(h->comm);
+        h->comm = nullptr;
+    }
+    h->built = false;
+    h->rank = 0;
+    h->world = 1;
+    AMIRA_TRY(comm_create(&h->comm, nccl_unique_id, rank, world));
+    if (!h->h_cnt) AMIRA_CUDA(cudaMallocHost((void **)&h->h_cnt, sizeof(long long) * ((size_t)MAX_WORLD * MAX_WORLD + 8)));
+    h->rank = rank;
+    h->world = world;
     return AMIRA_OK;
 }
 

@@ -137,6 +137,17 @@ __device__ __forceinline__ unsigned int node_insert(const BuildParams &P, const 
     return 0;
 }
 
+// hash of the canonical form of a window (dirneg: the window is the reverse complement of it)
+__device__ __forceinline__ unsigned long long canonical_hash(const int32_t *win, int k, int dirneg) {
+    unsigned long long h = 0x9e3779b97f4a7c15ULL;
+    for (int i = 0; i < k; ++i) {
+        int g = dirneg ? -win[k - 1 - i] : win[i];
+        h = (h ^ (unsigned long long)(unsigned int)g) * 0x100000001b3ULL;
+        h ^= h >> 29;
+    }
+    return mix64(h);
+}
+
 __device__ __forceinline__ void edge_insert(const BuildParams &P, unsigned long long key, unsigned long long ord) {
     const unsigned int cap = P.ecap;
     unsigned long long h = mix64(key);
@@ -226,13 +237,7 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
                     P.status[ST_ERR] = AMIRA_E_PALINDROME;  // construct_gene_mer.py:23-25
                 } else {
                     const int dirneg = dir < 0;
-                    unsigned long long h = 0x9e3779b97f4a7c15ULL;
-                    for (int i = 0; i < k; ++i) {
-                        int g = dirneg ? -win[k - 1 - i] : win[i];
-                        h = (h ^ (unsigned long long)(unsigned int)g) * 0x100000001b3ULL;
-                        h ^= h >> 29;
-                    }
-                    h = mix64(h);
+                    const unsigned long long h = canonical_hash(win, k, dirneg);
                     const unsigned long long mine =
                         ((h >> FP_SHIFT) << FP_SHIFT) | ((unsigned long long)p << 1) | (unsigned long long)dirneg;
                     const unsigned int slot = node_insert(P, win, dirneg, h, mine);

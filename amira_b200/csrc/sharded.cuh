@@ -1,0 +1,305 @@
+// sharded.cuh -- the multi-GPU half of the build (included by gmg.cu; one process per GPU).
+//
+// Reads are sharded contiguously in rank order, so the global first-seen order of upstream's dicts
+// (construct_graph.py:45-100) is the order of GLOBAL call positions call_base[rank] + p.  Each rank
+// first builds its local node / edge tables exactly as on one GPU (k_insert_windows).  Then:
+//
+//   nodes   one record per locally-unique gene-mer (canonical key, count, first global position,
+//           first direction) is routed to the owner rank hash(key) mod world with an all-to-all;
+//           the owner merges (sum of counts, minimum position) in a hash table; the merged
+//           records are all-gathered, sorted by first position = upstream's `_nodes` order, and
+//           every rank resolves its local nodes to global node indices through a lookup table.
+//   edges   the same with one record per locally-unique undirected adjacency, keyed on GLOBAL
+//           node indices (lo, hi, sd*td), carrying the pair count and the first pair event.
+//
+// Every rank ends with the identical global node / edge tables (adjacency and components are
+// computed redundantly on them: they are U-sized); per-read lists and the node -> read incidence
+// stay on the rank that owns the reads.  Exchange volume is O(locally unique), not O(windows).
+#pragma once
+
+namespace amira {
+
+constexpr int MAX_WORLD = 64;
+
+struct NodeRec {             // 16 B
+    unsigned long long ord;  // (global call position of the first window) << 1 | first window was the reverse complement
+    unsigned int cov;
+    unsigned int pad;
+};
+
+__device__ __forceinline__ int owner_of(unsigned long long h, int world) {
+    return (int)((((h >> 20) & 0xFFFFFull) * (unsigned long long)world) >> 20);
+}
+
+__device__ __forceinline__ void load_canonical(const int32_t *ids, unsigned long long word, int k, int32_t *out) {
+    const unsigned long long p = (word >> 1) & P_MASK;
+    const int neg = (int)(word & 1ull);
+    for (int j = 0; j < k; ++j) out[j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
+}
+
+// pass 1 / pass 2 over the local node table: count per owner, then scatter into the send buffer
+template <bool SCATTER>
+__global__ void k_node_route(NodeSlot *__restrict__ ntab, unsigned int ncap, const int32_t *__restrict__ ids, int k,
+                             int world, long long call_base, unsigned long long *__restrict__ counts,
+                             const long long *__restrict__ dest_off, int32_t *__restrict__ s_key,
+                             NodeRec *__restrict__ s_meta) {
+    __shared__ unsigned int s_cnt[MAX_WORLD];
+    if (!SCATTER) {
+        for (int i = threadIdx.x; i < world; i += blockDim.x) s_cnt[i] = 0;
+        __syncthreads();
+    }
+    const unsigned int stride = gridDim.x * blockDim.x;
+    int32_t key[MAX_K];
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ncap; s += stride) {
+        const unsigned long long w = ntab[s].word;
+        if (w == EMPTY64) continue;
+        load_canonical(ids, w, k, key);
+        const int d = owner_of(canonical_hash(key, k, 0), world);
+        if (!SCATTER) {
+            atomicAdd(&s_cnt[d], 1u);
+        } else {
+            const long long i = dest_off[d] + (long long)atomicAdd(&counts[d], 1ull);
+            for (int j = 0; j < k; ++j) s_key[i * k + j] = key[j];
+            NodeRec r;
+            r.ord = ((unsigned long long)(call_base + (long long)((w >> 1) & P_MASK)) << 1) | (w & 1ull);
+            r.cov = ntab[s].cov + 1u;
+            r.pad = 0;
+            s_meta[i] = r;
+            ntab[s].aux = (unsigned int)i;
+        }
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < world; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
+    }
+}
+
+__global__ void k_rec_ord_keys(const NodeRec *__restrict__ meta, long long n, unsigned long long *__restrict__ keys,
+                               unsigned int *__restrict__ idx) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = meta[i].ord;
+        idx[i] = (unsigned int)i;
+    }
+}
+
+__global__ void k_gather_node_recs(const unsigned int *__restrict__ perm, const int32_t *__restrict__ in_key,
+                                   const NodeRec *__restrict__ in_meta, int k, long long n,
+                                   int32_t *__restrict__ out_key, NodeRec *__restrict__ out_meta) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long s = perm[i];
+    for (int j = 0; j < k; ++j) out_key[i * k + j] = in_key[s * k + j];
+    out_meta[i] = in_meta[s];
+}
+
+// records (canonical keys, k ids each, sorted by first position) -> table; the slot keeps the
+// smallest record index (= earliest first position) and the weighted count
+__global__ void k_insert_records(const BuildParams P, long long n, const NodeRec *__restrict__ meta) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int32_t *win = P.ids + r * P.k;
+    const unsigned long long h = canonical_hash(win, P.k, 0);
+    const unsigned long long mine = ((h >> FP_SHIFT) << FP_SHIFT) | ((unsigned long long)(r * P.k) << 1);
+    const unsigned int slot = node_insert(P, win, 0, h, mine);
+    if (meta) atomicAdd(&P.ntab[slot].cov, meta[r].cov);
+}
+
+__global__ void k_pack_merged_nodes(const NodeSlot *__restrict__ tab, unsigned int cap, const int32_t *__restrict__ keys,
+                                    const NodeRec *__restrict__ meta, int k, unsigned long long *__restrict__ counter,
+                                    int32_t *__restrict__ out_key, NodeRec *__restrict__ out_meta) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride) {
+        const unsigned long long w = tab[s].word;
+        if (w == EMPTY64) continue;
+        const long long r = (long long)(((w >> 1) & P_MASK) / (unsigned long long)k);
+        const long long i = (long long)atomicAdd(counter, 1ull);
+        for (int j = 0; j < k; ++j) out_key[i * k + j] = keys[r * k + j];
+        NodeRec o;
+        o.ord = meta[r].ord;
+        o.cov = tab[s].cov + 1u;   // counts from 0xFFFFFFFF: the sum of the merged weights
+        o.pad = 0;
+        out_meta[i] = o;
+    }
+}
+
+__global__ void k_finalize_nodes(const unsigned int *__restrict__ perm, const int32_t *__restrict__ g_key,
+                                 const NodeRec *__restrict__ g_meta, int k, long long n, int32_t *__restrict__ node_key,
+                                 uint32_t *__restrict__ node_cov, int8_t *__restrict__ node_dir,
+                                 int32_t *__restrict__ parent) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long s = perm[i];
+    for (int j = 0; j < k; ++j) node_key[i * k + j] = g_key[s * k + j];
+    node_cov[i] = g_meta[s].cov;
+    node_dir[i] = (g_meta[s].ord & 1ull) ? -1 : 1;
+    parent[i] = (int32_t)i;
+}
+
+// find-only probe of a record table (every key looked up is present by construction)
+__device__ __forceinline__ long long node_lookup(const BuildParams &P, const int32_t *win) {
+    const unsigned int cap = P.ncap;
+    const int k = P.k;
+    const unsigned long long h = canonical_hash(win, k, 0);
+    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
+    const unsigned int fp = (unsigned int)(h >> FP_SHIFT);
+    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+        const unsigned long long cur = P.ntab[s].word;
+        if (cur == EMPTY64) break;
+        if ((unsigned int)(cur >> FP_SHIFT) == fp) {
+            const long long q = (long long)((cur >> 1) & P_MASK);
+            bool same = true;
+            for (int j = 0; j < k; ++j)
+                if (win[j] != P.ids[q + j]) {
+                    same = false;
+                    break;
+                }
+            if (same) return q / k;
+        }
+        if (++s == cap) s = 0;
+    }
+    P.status[ST_ERR] = AMIRA_E_STATE;
+    return 0;
+}
+
+// local node table: aux (index into the send buffer) -> global node index; local coverage per global node
+__global__ void k_local_to_global(NodeSlot *__restrict__ ntab, unsigned int ncap, const int32_t *__restrict__ s_key,
+                                  const BuildParams G, uint32_t *__restrict__ cov_local) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ncap; s += stride) {
+        if (ntab[s].word == EMPTY64) continue;
+        const long long i = ntab[s].aux;
+        const long long g = node_lookup(G, s_key + i * G.k);
+        ntab[s].aux = (unsigned int)g;
+        cov_local[g] = ntab[s].cov + 1u;
+    }
+}
+
+// ---- edges ----------------------------------------------------------------------------------------
+__device__ __forceinline__ EdgeSlot global_edge_record(const EdgeSlot &e, const NodeSlot *__restrict__ ntab,
+                                                      long long call_base) {
+    const unsigned int lo = (unsigned int)(e.key >> 32), hi = (unsigned int)((e.key & 0xFFFFFFFFull) >> 1);
+    const bool src_hi = (e.ord >> 1) & 1ull;
+    const unsigned int gs = ntab[src_hi ? hi : lo].aux, gt = ntab[src_hi ? lo : hi].aux;
+    EdgeSlot r;
+    r.key = ((unsigned long long)min(gs, gt) << 32) | ((unsigned long long)max(gs, gt) << 1) | (e.key & 1ull);
+    r.ord = ((unsigned long long)(call_base + (long long)(e.ord >> 2)) << 2) | ((unsigned long long)(gs > gt) << 1) |
+            (e.ord & 1ull);
+    r.cov = e.cov + 1u;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    return r;
+}
+
+template <bool SCATTER>
+__global__ void k_edge_route(const EdgeSlot *__restrict__ etab, unsigned int ecap, const NodeSlot *__restrict__ ntab,
+                             int world, long long call_base, unsigned long long *__restrict__ counts,
+                             const long long *__restrict__ dest_off, EdgeSlot *__restrict__ s_edges) {
+    __shared__ unsigned int s_cnt[MAX_WORLD];
+    if (!SCATTER) {
+        for (int i = threadIdx.x; i < world; i += blockDim.x) s_cnt[i] = 0;
+        __syncthreads();
+    }
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ecap; s += stride) {
+        EdgeSlot e = etab[s];
+        if (e.key == EMPTY64) continue;
+        const EdgeSlot r = global_edge_record(e, ntab, call_base);
+        const int d = owner_of(mix64(r.key), world);
+        if (!SCATTER) atomicAdd(&s_cnt[d], 1u);
+        else s_edges[dest_off[d] + (long long)atomicAdd(&counts[d], 1ull)] = r;
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < world; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
+    }
+}
+
+__global__ void k_merge_edges(const EdgeSlot *__restrict__ recs, long long n, EdgeSlot *__restrict__ tab,
+                              unsigned int cap, int *__restrict__ status) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const EdgeSlot r = recs[i];
+    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)mix64(r.key) * cap) >> 32);
+    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+        unsigned long long cur = tab[s].key;
+        if (cur == EMPTY64) {
+            unsigned long long old = atomicCAS(&tab[s].key, EMPTY64, r.key);
+            cur = (old == EMPTY64) ? r.key : old;
+        }
+        if (cur == r.key) {
+            atomicMin(&tab[s].ord, r.ord);
+            atomicAdd(&tab[s].cov, r.cov);
+            return;
+        }
+        if (++s == cap) s = 0;
+    }
+    status[ST_OVERFLOW_E] = 1;
+}
+
+__global__ void k_pack_merged_edges(const EdgeSlot *__restrict__ tab, unsigned int cap,
+                                    unsigned long long *__restrict__ counter, EdgeSlot *__restrict__ out) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride) {
+        EdgeSlot e = tab[s];
+        if (e.key == EMPTY64) continue;
+        e.cov += 1u;   // counts from 0xFFFFFFFF: the sum of the merged pair counts
+        out[atomicAdd(counter, 1ull)] = e;
+    }
+}
+
+__global__ void k_edge_ord_keys(const EdgeSlot *__restrict__ recs, long long n, unsigned long long *__restrict__ keys,
+                                unsigned int *__restrict__ idx) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = recs[i].ord;
+        idx[i] = (unsigned int)i;
+    }
+}
+
+// directed edges per undirected record, in first-pair order (2, or 1 for a self edge)
+__global__ void k_edge_fanout(const unsigned int *__restrict__ perm, const EdgeSlot *__restrict__ recs, long long n,
+                              int *__restrict__ cnt) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned long long key = recs[perm[i]].key;
+        cnt[i] = ((unsigned int)(key >> 32) == (unsigned int)((key & 0xFFFFFFFFull) >> 1)) ? 1 : 2;
+    } else if (i == n) {
+        cnt[i] = 0;
+    }
+}
+
+__global__ void k_emit_edges_sorted(const unsigned int *__restrict__ perm, const EdgeSlot *__restrict__ recs,
+                                    const int *__restrict__ pref, long long n, int32_t *__restrict__ e_src,
+                                    int32_t *__restrict__ e_tgt, int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td,
+                                    uint32_t *__restrict__ e_cov, int32_t *__restrict__ parent) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const EdgeSlot e = recs[perm[i]];
+    const int idx = pref[i];
+    const unsigned int lo = (unsigned int)(e.key >> 32), hi = (unsigned int)((e.key & 0xFFFFFFFFull) >> 1);
+    const int rel = (e.key & 1ull) ? 1 : -1;
+    const bool src_hi = (e.ord >> 1) & 1ull;
+    const int src = (int)(src_hi ? hi : lo), tgt = (int)(src_hi ? lo : hi);
+    const int sd = (e.ord & 1ull) ? -1 : 1, td = rel * sd;
+    if (lo != hi) {
+        e_src[idx] = src; e_tgt[idx] = tgt; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = e.cov;
+        e_src[idx + 1] = tgt; e_tgt[idx + 1] = src; e_sd[idx + 1] = (int8_t)-td; e_td[idx + 1] = (int8_t)-sd;
+        e_cov[idx + 1] = e.cov;
+        uf_union(parent, src, tgt);
+    } else {
+        e_src[idx] = src; e_tgt[idx] = src; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = 2u * e.cov;
+    }
+}
+
+__global__ void k_add_i32(int32_t *__restrict__ a, long long n, int32_t v) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] += v;
+}
+
+__global__ void k_set_w(const int64_t *__restrict__ win_off, int64_t R, long long *__restrict__ sizes) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sizes[SZ_W] = win_off[R];
+}
+
+}  // namespace amira

@@ -132,13 +132,17 @@ int amira_gmg_filter(amira_gmg *h, uint32_t min_node_cov, uint32_t min_edge_cov)
 int amira_gmg_filter_mask_sizes(amira_gmg *h, int64_t *n_nodes_before, int64_t *n_edges_before);
 int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edge_keep);
 
-/* Multi-GPU (one process per GPU): reads are sharded contiguously over ranks, canonical gene-mers
- * are owned by hash range, partial tables are routed with an NCCL all-to-all.  nccl_unique_id is
- * the 128-byte ncclUniqueId of rank 0.  After comm_init, amira_gmg_build takes this rank's shard and
- * first_read_global (amira_gmg_set_shard) and every rank ends with the global node / edge tables. */
+/* Multi-GPU (one process per GPU; no upstream counterpart -- upstream's joblib fan-out,
+ * graph_utils.py:105-124, is disabled at every call site).  The globally ordered read set is
+ * sharded contiguously over ranks in rank order; canonical gene-mers and edges are owned by hash
+ * range and the partial tables are routed with NCCL all-to-alls.  nccl_unique_id is the 128-byte
+ * ncclUniqueId created by rank 0 (amira_gmg_nccl_unique_id) and distributed by the caller.  After
+ * comm_init every amira_gmg_build is COLLECTIVE: each rank passes its own shard, and ends with the
+ * identical global node / edge tables (exports as on one GPU); the per-read exports and the
+ * node -> read incidence cover the rank's own reads, read indices are global.  Filters are
+ * collective-free (every rank applies them to the replicated tables). */
 int amira_gmg_nccl_unique_id(void *out_128_bytes);
 int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int world);
-int amira_gmg_set_shard(amira_gmg *h, int64_t first_read_global, int64_t first_call_global);
 
 /* Micro-benchmark for the atomic roofline: random-address 32-bit RED.ADD and 64-bit
  * CAS into a table of table_bytes; returns operations per second of each. */
