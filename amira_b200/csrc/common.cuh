@@ -66,7 +66,7 @@ struct DevBuf {
 };
 
 // ---- table layouts -----------------------------------------------------------------------------
-// Node table slot (16 B, two per 32 B sector).  `word` packs, from the top: a 22-bit fingerprint
+// Node table slot (32 B, one sector).  `word` packs, from the top: a 22-bit fingerprint
 // of the canonical gene-mer, the 41-bit global call index p of the FIRST window seen with this
 // gene-mer, and one bit that is set when that first window was the reverse complement of the
 // canonical form.  Because the fingerprint is a function of the key, atomicMin over words of one
@@ -74,12 +74,15 @@ struct DevBuf {
 // which is upstream's dict insertion order, and carries that occurrence's direction.
 // The key itself is not stored: it is ids[p .. p+k) (reverse-complemented when the bit is set).
 // `cov` counts from 0xFFFFFFFF so that the whole table is initialised by one memset(0xFF).
-struct NodeSlot {
+// klo / khi: the canonical gene-mer packed into 2 x 62 bits (when it fits), published by the thread
+// that claimed the slot; all-ones = not (yet) published.
+struct __align__(32) NodeSlot {
     unsigned long long word;
     unsigned int cov;  // occurrences - 1
     unsigned int aux;  // node index once the first-seen order is known
+    unsigned long long klo, khi;
 };
-static_assert(sizeof(NodeSlot) == 16, "NodeSlot must be 16 bytes");
+static_assert(sizeof(NodeSlot) == 32, "NodeSlot must be 32 bytes (one sector)");
 
 constexpr unsigned long long EMPTY64 = ~0ull;
 constexpr int P_BITS = 41;
@@ -95,7 +98,7 @@ constexpr unsigned int FP_MAX = (1u << (64 - FP_SHIFT)) - 2;  // all-ones is res
 // | sd < 0) of the first pair event (atomicMin), from which both directed edges, their creation
 // order (forward then reverse) and their stored directions follow.  S == T collapses to one
 // directed edge with twice the count.
-struct EdgeSlot {
+struct __align__(32) EdgeSlot {
     unsigned long long key;  // lo << 32 | hi << 1 | (rel > 0)
     unsigned long long ord;
     unsigned int cov;  // pair events - 1

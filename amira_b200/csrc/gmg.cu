@@ -29,6 +29,7 @@ struct amira_gmg {
     bool own_stream = false;
     int n_sm = 148;
     int insert_ctas_per_sm = 1;
+    int unpack_bits_failed = 0;  // widest packed-key width that did not fit this handle's gene ids
 
     // input (owned copy or borrowed device pointers)
     DevBuf d_ids, d_off, d_ps, d_pe;
@@ -52,7 +53,7 @@ struct amira_gmg {
     // nodes (cur) and compaction targets (alt)
     DevBuf node_key, node_cov, node_dir, node_comp, reads_off, reads;
     DevBuf node_key2, node_cov2, node_dir2, node_comp2, reads_off2, reads2;
-    DevBuf parent, is_root;
+    DevBuf parent, is_root, cc_min;
     // edges
     DevBuf e_src, e_tgt, e_sd, e_td, e_cov;
     DevBuf e_src2, e_tgt2, e_sd2, e_td2, e_cov2;
@@ -235,6 +236,11 @@ int do_build(amira_gmg *h) {
     if (h->hint_edges > 0) ecap = h->hint_edges * 2 + 1024;
     else if (h->prev_G > 0 && G <= 4 * h->prev_G)
         ecap = (int64_t)((double)h->prev_und_edges * ((double)G / (double)h->prev_G) * 2.0) + 4096;
+    // gene-mers of up to 124 bits are packed into the node slot: 124 / k bits per signed gene id.
+    // If an id does not fit (seen by the kernel while staging), the build is redone unpacked and the
+    // handle remembers the width that failed.
+    int key_bits = std::min(32, 124 / k);
+    if (key_bits < 8 || key_bits <= h->unpack_bits_failed) key_bits = 0;
     for (int attempt = 0;; ++attempt) {
         ncap = std::min<int64_t>(ncap, 0x7FFFFFF0ll);
         ecap = std::min<int64_t>(ecap, 0x7FFFFFF0ll);
@@ -259,9 +265,15 @@ int do_build(amira_gmg *h) {
                 P.win_end = h->has_pos ? h->win_end.as<int32_t>() : nullptr;
                 P.status = h->d_status.as<int>();
                 P.read_base = h->first_read_global;
-                const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sm * h->insert_ctas_per_sm);
+                P.key_bits = key_bits;
+                P.ids_aligned = (reinterpret_cast<uintptr_t>(h->ids) & 15) == 0;
+                const int grid = (int)std::min<int64_t>((n_tiles + INS_WARPS - 1) / INS_WARPS,
+                                                        (int64_t)h->n_sm * h->insert_ctas_per_sm);
                 Phase phk(h, AMIRA_PH_INSERT_KERNEL);
-                LAUNCH(h, k_insert_windows, grid, INS_THREADS, P);
+                if (k == 3) LAUNCH(h, k_insert_windows<3>, grid, INS_THREADS, P);
+                else if (k == 5) LAUNCH(h, k_insert_windows<5>, grid, INS_THREADS, P);
+                else if (k == 7) LAUNCH(h, k_insert_windows<7>, grid, INS_THREADS, P);
+                else LAUNCH(h, k_insert_windows<0>, grid, INS_THREADS, P);
             }
         }
         if (h->world > 1) {
@@ -282,7 +294,12 @@ int do_build(amira_gmg *h) {
         AMIRA_TRY(fetch_status_sizes(h));
         if (h->h_status[ST_ERR]) break;
         const bool ovn = h->h_status[ST_OVERFLOW_N], ove = h->h_status[ST_OVERFLOW_E];
-        if (!ovn && !ove) break;
+        const bool unpack = h->h_status[ST_UNPACK] && key_bits > 0;
+        if (unpack) {
+            h->unpack_bits_failed = std::max(h->unpack_bits_failed, key_bits);
+            key_bits = 0;
+        }
+        if (!ovn && !ove && !unpack) break;
         if (attempt >= 6) {
             set_error("hash tables overflowed after %d attempts (ncap=%lld ecap=%lld)", attempt + 1, (long long)ncap,
                       (long long)ecap);
@@ -389,10 +406,16 @@ int do_build(amira_gmg *h) {
     // ---- components
     {
         Phase ph(h, AMIRA_PH_COMPONENTS);
-        LAUNCH(h, k_cc_roots, grid_for(N + 1, 256), 256, h->parent.as<int32_t>(), N, h->is_root.as<int>());
+        AMIRA_TRY(h->cc_min.reserve(sizeof(unsigned int) * (N + 1)));
+        AMIRA_CUDA(cudaMemsetAsync(h->cc_min.p, 0xFF, sizeof(unsigned int) * (N + 1), st));
+        if (N > 0)
+            LAUNCH(h, k_cc_flatten, grid_for(N, 256), 256, h->parent.as<int32_t>(), N, h->cc_min.as<unsigned int>(),
+                   h->node_comp.as<uint32_t>());
+        LAUNCH(h, k_cc_first, grid_for(N + 1, 256), 256, h->node_comp.as<uint32_t>(), h->cc_min.as<unsigned int>(), N,
+               h->is_root.as<int>());
         AMIRA_TRY(exclusive_sum_inplace(h, h->is_root.as<int>(), N + 1));
         if (N > 0)
-            LAUNCH(h, k_cc_number, grid_for(N, 256), 256, h->parent.as<int32_t>(), h->is_root.as<int>(), N,
+            LAUNCH(h, k_cc_number, grid_for(N, 256), 256, h->cc_min.as<unsigned int>(), h->is_root.as<int>(), N,
                    h->node_comp.as<uint32_t>());
     }
     h->n_comps = N;  // upper bound on component ids (ids are <= number of nodes)
@@ -774,7 +797,7 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     AMIRA_CUDA(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
     int occ = 1;
-    AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_insert_windows, INS_THREADS, 0));
+    AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_insert_windows<5>, INS_THREADS, 0));
     h->insert_ctas_per_sm = std::max(1, occ);
     AMIRA_TRY(h->d_status.reserve(sizeof(int) * ST_COUNT));
     AMIRA_TRY(h->d_sizes.reserve(sizeof(long long) * SZ_COUNT));
@@ -802,7 +825,7 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->d_nsel, &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rkey2, &h->x_rmeta2,
                       &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_sortk, &h->x_sortk2, &h->x_sorti,
                       &h->x_sorti2, &h->x_sedge, &h->x_redge, &h->x_medge, &h->x_gedge, &h->x_etab, &h->x_fan,
-                      &h->cov_local};
+                      &h->cov_local, &h->cc_min};
     for (DevBuf *b : bufs) b->release();
     if (h->comm) comm_destroy(h->comm);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);

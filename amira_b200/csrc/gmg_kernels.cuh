@@ -32,14 +32,15 @@
 namespace amira {
 
 constexpr int INS_THREADS = 256;
-constexpr int INS_ITEMS = 4;
-constexpr int INS_TILE = INS_THREADS * INS_ITEMS;  // calls per tile
+constexpr int INS_WARPS = INS_THREADS / 32;
+constexpr int WC = 128;        // calls per warp chunk
+constexpr int INS_TILE = WC;   // granularity of the chunk -> first read map
 constexpr int MAX_K = 64;
-constexpr int NR_CAP = INS_TILE + 2;               // reads whose offsets are cached per tile
+constexpr int NR_STAGE = 30;   // reads of a chunk whose offsets are staged in shared memory
 constexpr unsigned int INVALID_VAL = 0xFFFFFFFFu;
 constexpr unsigned int MAX_PROBES = 1u << 15;
 
-enum { ST_ERR = 0, ST_OVERFLOW_N = 1, ST_OVERFLOW_E = 2, ST_COUNT = 4 };
+enum { ST_ERR = 0, ST_OVERFLOW_N = 1, ST_OVERFLOW_E = 2, ST_UNPACK = 3, ST_COUNT = 4 };
 enum { SZ_W = 0, SZ_NODES = 1, SZ_EDGES = 2, SZ_INC = 3, SZ_SHORT = 4, SZ_FW = 5, SZ_BW = 6, SZ_COUNT = 8 };
 
 struct BuildParams {
@@ -62,6 +63,8 @@ struct BuildParams {
     int32_t *win_end;
     int *status;
     int64_t read_base;  // global index of this shard's first read (multi-GPU)
+    int key_bits;       // bits per gene of the packed 124-bit key; 0: gene-mers are compared through ids
+    int ids_aligned;    // ids is 16-byte aligned (128-bit staging loads)
 };
 
 __host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
@@ -99,44 +102,6 @@ __global__ void k_read_windows(const int64_t *__restrict__ off, int64_t R, int k
 }
 
 // ---------------------------------------------------------------------------------------------
-// node table insert-or-find.  win = the window's k ids in shared memory.
-__device__ __forceinline__ unsigned int node_insert(const BuildParams &P, const int32_t *win, int dirneg,
-                                                    unsigned long long h, unsigned long long mine) {
-    const unsigned int cap = P.ncap;
-    const int k = P.k;
-    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
-    const unsigned int fp = (unsigned int)(mine >> FP_SHIFT);
-    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
-        unsigned long long cur = __ldcg(&P.ntab[s].word);
-        if (cur == EMPTY64) {
-            unsigned long long old = atomicCAS(&P.ntab[s].word, EMPTY64, mine);
-            if (old == EMPTY64) return s;
-            cur = old;
-        }
-        if ((unsigned int)(cur >> FP_SHIFT) == fp) {
-            // same fingerprint: compare against the slot's representative window in the input
-            const int64_t q = (int64_t)((cur >> 1) & P_MASK);
-            const int qneg = (int)(cur & 1ull);
-            bool same = true;
-            for (int j = 0; j < k; ++j) {
-                int a = dirneg ? -win[k - 1 - j] : win[j];
-                int b = qneg ? -__ldg(P.ids + q + (k - 1 - j)) : __ldg(P.ids + q + j);
-                if (a != b) {
-                    same = false;
-                    break;
-                }
-            }
-            if (same) {
-                if (mine < cur) atomicMin(&P.ntab[s].word, mine);  // keep the first occurrence
-                return s;
-            }
-        }
-        if (++s == cap) s = 0;
-    }
-    P.status[ST_OVERFLOW_N] = 1;
-    return 0;
-}
-
 // hash of the canonical form of a window (dirneg: the window is the reverse complement of it)
 __device__ __forceinline__ unsigned long long canonical_hash(const int32_t *win, int k, int dirneg) {
     unsigned long long h = 0x9e3779b97f4a7c15ULL;
@@ -148,18 +113,95 @@ __device__ __forceinline__ unsigned long long canonical_hash(const int32_t *win,
     return mix64(h);
 }
 
+__device__ __forceinline__ unsigned long long packed_hash(unsigned long long klo, unsigned long long khi) {
+    unsigned long long h = (klo * 0x9E3779B97F4A7C15ULL) ^ ((khi + 0x632BE59BD9B4E019ULL) * 0xC2B2AE3D27D4EB4FULL);
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ULL;
+    h ^= h >> 29;
+    return h;
+}
+
+// one 256-bit load of a node slot (LDG.E.256): word, cov|aux, packed key halves
+__device__ __forceinline__ void load_node_slot(const NodeSlot *s, unsigned long long &word, unsigned long long &ca,
+                                               unsigned long long &klo, unsigned long long &khi) {
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(word), "=l"(ca), "=l"(klo), "=l"(khi) : "l"(s));
+}
+
+__device__ __forceinline__ void publish_key(NodeSlot *s, unsigned long long klo, unsigned long long khi) {
+    asm volatile("st.global.cg.v2.u64 [%0], {%1,%2};" ::"l"(&s->klo), "l"(klo), "l"(khi) : "memory");
+}
+
+__device__ __forceinline__ void load_edge_slot(const EdgeSlot *s, unsigned long long &key, unsigned long long &ord) {
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(key), "=l"(ord) : "l"(s));
+}
+
+// compare a window (canonical form given by win / dirneg) with the representative window of a slot
+__device__ __forceinline__ bool same_as_representative(const BuildParams &P, const int32_t *win, int dirneg,
+                                                       unsigned long long cur) {
+    const int k = P.k;
+    const int64_t q = (int64_t)((cur >> 1) & P_MASK);
+    const int qneg = (int)(cur & 1ull);
+    for (int j = 0; j < k; ++j) {
+        int a = dirneg ? -win[k - 1 - j] : win[j];
+        int b = qneg ? -__ldg(P.ids + q + (k - 1 - j)) : __ldg(P.ids + q + j);
+        if (a != b) return false;
+    }
+    return true;
+}
+
+// Node table insert-or-find.  The slot is claimed by a CAS on `word` (fingerprint | first call
+// position | first direction); the winner then publishes the packed 124-bit key in the same 32-byte
+// sector, so that every later visitor decides "same gene-mer?" from the one sector it loaded.
+// Until the key is published (or when the gene-mer does not fit 124 bits: packed == false) the
+// comparison falls back to the representative window ids[p .. p+k) named by `word`.
+__device__ __forceinline__ unsigned int node_insert(const BuildParams &P, const int32_t *win, int dirneg, bool packed,
+                                                    unsigned long long klo, unsigned long long khi,
+                                                    unsigned long long h, unsigned long long mine) {
+    const unsigned int cap = P.ncap;
+    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
+    const unsigned int fp = (unsigned int)(mine >> FP_SHIFT);
+    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+        unsigned long long cur, ca, sl, sh;
+        load_node_slot(&P.ntab[s], cur, ca, sl, sh);
+        if (cur == EMPTY64) {
+            unsigned long long old = atomicCAS(&P.ntab[s].word, EMPTY64, mine);
+            if (old == EMPTY64) {
+                if (packed) publish_key(&P.ntab[s], klo, khi);
+                return s;
+            }
+            cur = old;
+            sl = sh = EMPTY64;
+        }
+        bool same;
+        if (packed && sl != EMPTY64 && sh != EMPTY64) same = (sl == klo) & (sh == khi);
+        else same = ((unsigned int)(cur >> FP_SHIFT) == fp) && same_as_representative(P, win, dirneg, cur);
+        if (same) {
+            if (mine < cur) atomicMin(&P.ntab[s].word, mine);  // keep the first occurrence
+            return s;
+        }
+        if (++s == cap) s = 0;
+    }
+    P.status[ST_OVERFLOW_N] = 1;
+    return 0;
+}
+
 __device__ __forceinline__ void edge_insert(const BuildParams &P, unsigned long long key, unsigned long long ord) {
     const unsigned int cap = P.ecap;
-    unsigned long long h = mix64(key);
-    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
+    unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ULL;
+    unsigned int s = (unsigned int)(h >> 32);
+    s = (unsigned int)(((unsigned long long)s * cap) >> 32);
     for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
-        unsigned long long cur = __ldcg(&P.etab[s].key);
+        unsigned long long cur, cord;
+        load_edge_slot(&P.etab[s], cur, cord);
         if (cur == EMPTY64) {
             unsigned long long old = atomicCAS(&P.etab[s].key, EMPTY64, key);
             cur = (old == EMPTY64) ? key : old;
+            cord = EMPTY64;
         }
         if (cur == key) {
-            if (ord < __ldcg(&P.etab[s].ord)) atomicMin(&P.etab[s].ord, ord);
+            if (ord < cord) atomicMin(&P.etab[s].ord, ord);
             atomicAdd(&P.etab[s].cov, 1u);
             return;
         }
@@ -168,84 +210,161 @@ __device__ __forceinline__ void edge_insert(const BuildParams &P, unsigned long 
     P.status[ST_OVERFLOW_E] = 1;
 }
 
-__global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParams P) {
-    __shared__ __align__(16) int32_t s_ids[INS_TILE + MAX_K + 4];
-    __shared__ unsigned int s_val[INS_TILE + 1];  // slot | dirneg << 31 per window start, INVALID_VAL if none
-    __shared__ int s_j[INS_TILE];                 // read (relative to the tile's first read) of each call
-    __shared__ long long s_off[NR_CAP + 1];
-    __shared__ long long s_woff[NR_CAP];
-    typedef cub::BlockScan<int, INS_THREADS> Scan;
-    __shared__ typename Scan::TempStorage s_scan;
+// per-warp staging area: one 128-call chunk (+ halo) and what the lanes exchange about it
+struct __align__(16) WarpStage {
+    int32_t ids[WC + MAX_K + 4];
+    int j[WC];                 // read (relative to the chunk's first read) of each call
+    unsigned int val[WC + 4];  // slot | dirneg << 31 per window start, INVALID_VAL if none
+    long long off[NR_STAGE + 2];
+    long long woff[NR_STAGE + 1];
+};
 
-    const int tid = threadIdx.x;
-    const int k = P.k;
-    for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const int64_t t0 = tile * INS_TILE;
-        const int len = (int)imin64(INS_TILE, P.G - t0);
-        const int n_load = (int)imin64(len + k, P.G - t0);
-        const int r_lo = P.tile_r0[tile];
-        const int r_hi = (tile + 1 < P.n_tiles) ? P.tile_r0[tile + 1] : (int)(P.R - 1);
+// THE hot kernel.  One warp per 128-call chunk, no block-level barriers: every warp stages its chunk
+// (+k halo) with 128-bit loads, finds the read of every call with a warp max-scan over the read
+// starts that fall in the chunk, canonicalises / packs / hashes each window, inserts into the node
+// table, writes the per-window outputs, and inserts the adjacent-pair edges from the slot numbers
+// it staged in shared memory.  K > 0: gene-mer size known at compile time (windows in registers).
+template <int K>
+__global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParams P) {
+    __shared__ WarpStage s_stage[INS_WARPS];
+    const int lane = threadIdx.x & 31;
+    WarpStage &S = s_stage[threadIdx.x >> 5];
+    const int k = K ? K : P.k;
+    const int kb = P.key_bits;
+    const bool packed = kb > 0;
+    const int64_t n_warps = (int64_t)gridDim.x * INS_WARPS;
+    for (int64_t c = (int64_t)blockIdx.x * INS_WARPS + (threadIdx.x >> 5); c < P.n_tiles; c += n_warps) {
+        const int64_t c0 = c * WC;
+        const int len = (int)imin64(WC, P.G - c0);
+        const int n_load = (int)imin64(len + k, P.G - c0);
+        const int r_lo = P.tile_r0[c];
+        const int r_hi = (c + 1 < P.n_tiles) ? P.tile_r0[c + 1] : (int)(P.R - 1);
         const int nr = r_hi - r_lo + 1;
 
-        // ---- stage the tile (+ halo) with 128-bit loads; t0 is a multiple of 1024 calls
+        // ---- stage the chunk (+ halo); c0 is a multiple of 128 calls
         {
-            const int32_t *src = P.ids + t0;
-            const int n4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (n_load >> 2) : 0;
-            const int4 *src4 = reinterpret_cast<const int4 *>(src);
-            int4 *dst4 = reinterpret_cast<int4 *>(s_ids);
-            for (int i = tid; i < n4; i += INS_THREADS) dst4[i] = __ldg(src4 + i);
-            for (int i = (n4 << 2) + tid; i < n_load; i += INS_THREADS) s_ids[i] = __ldg(src + i);
+            const int32_t *src = P.ids + c0;
+            bool bad = false;
+            const int i4 = lane * 4;
+            if (P.ids_aligned && i4 + 4 <= n_load) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(src) + lane);
+                *reinterpret_cast<int4 *>(&S.ids[i4]) = v;
+                if (packed && kb < 32) {
+                    const unsigned int bias = 1u << (kb - 1), lim = 1u << kb;
+                    bad = ((unsigned int)v.x + bias >= lim) | ((unsigned int)v.y + bias >= lim) |
+                          ((unsigned int)v.z + bias >= lim) | ((unsigned int)v.w + bias >= lim);
+                }
+            } else {
+                for (int i = i4; i < i4 + 4 && i < n_load; ++i) {
+                    const int g = __ldg(src + i);
+                    S.ids[i] = g;
+                    if (packed && kb < 32) bad |= ((unsigned int)g + (1u << (kb - 1)) >= (1u << kb));
+                }
+            }
+            for (int i = WC + lane; i < n_load; i += 32) {
+                const int g = __ldg(src + i);
+                S.ids[i] = g;
+                if (packed && kb < 32) bad |= ((unsigned int)g + (1u << (kb - 1)) >= (1u << kb));
+            }
+            if (bad) P.status[ST_UNPACK] = 1;  // an id does not fit the packed key: the host retries unpacked
         }
-        for (int i = tid; i < INS_TILE; i += INS_THREADS) s_j[i] = 0;
-        for (int i = tid; i <= nr && i <= NR_CAP; i += INS_THREADS) s_off[i] = P.off[r_lo + i];
-        for (int i = tid; i < nr && i < NR_CAP; i += INS_THREADS) s_woff[i] = P.win_off[r_lo + i];
-        __syncthreads();
+        *reinterpret_cast<int4 *>(&S.j[lane * 4]) = make_int4(0, 0, 0, 0);
+        for (int i = lane; i <= nr && i <= NR_STAGE + 1; i += 32) S.off[i] = P.off[r_lo + i];
+        for (int i = lane; i < nr && i <= NR_STAGE; i += 32) S.woff[i] = P.win_off[r_lo + i];
+        __syncwarp();
         // ---- read boundaries: mark each later read's first call, then an inclusive max-scan
-        for (int j = 1 + tid; j < nr; j += INS_THREADS) {
-            long long o = (j <= NR_CAP ? s_off[j] : P.off[r_lo + j]) - t0;
-            if (o < len) atomicMax(&s_j[(int)o], j);
+        for (int j = 1 + lane; j < nr; j += 32) {
+            const long long o = (j <= NR_STAGE + 1 ? S.off[j] : P.off[r_lo + j]) - c0;
+            if (o < len) atomicMax(&S.j[(int)o], j);
         }
-        __syncthreads();
+        __syncwarp();
         {
-            int items[INS_ITEMS];
+            int4 v = *reinterpret_cast<int4 *>(&S.j[lane * 4]);
+            v.y = max(v.x, v.y);
+            v.z = max(v.y, v.z);
+            v.w = max(v.z, v.w);
+            int incl = v.w;
 #pragma unroll
-            for (int i = 0; i < INS_ITEMS; ++i) items[i] = s_j[tid * INS_ITEMS + i];
-            Scan(s_scan).InclusiveScan(items, items, MaxOp());
-#pragma unroll
-            for (int i = 0; i < INS_ITEMS; ++i) s_j[tid * INS_ITEMS + i] = items[i];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl = max(incl, o);
+            }
+            int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0;
+            v.x = max(v.x, excl);
+            v.y = max(v.y, excl);
+            v.z = max(v.z, excl);
+            v.w = max(v.w, excl);
+            *reinterpret_cast<int4 *>(&S.j[lane * 4]) = v;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- windows: pl == len is the halo window that only serves the last pair of the tile
-        for (int pl = tid; pl <= len; pl += INS_THREADS) {
+        // ---- windows: pl == len is the halo window that only serves the last pair of the chunk
+#pragma unroll 1
+        for (int pl = lane; pl <= len; pl += 32) {
             const bool halo = (pl == len);
-            const int j = s_j[halo ? pl - 1 : pl];
-            const int64_t p = t0 + pl;
-            const long long re = (j + 1 <= NR_CAP) ? s_off[j + 1] : P.off[r_lo + j + 1];
+            const int j = S.j[halo ? pl - 1 : pl];
+            const int64_t p = c0 + pl;
+            const long long re = (j <= NR_STAGE) ? S.off[j + 1] : P.off[r_lo + j + 1];
             unsigned int val = INVALID_VAL;
             if (p + k <= re) {
-                const int32_t *win = s_ids + pl;
+                const int32_t *win = S.ids + pl;
                 int dir = 0;
-                for (int i = 0; i < k; ++i) {
-                    int f = win[i], c = -win[k - 1 - i];
-                    if (f != c) {
-                        dir = f < c ? 1 : -1;
-                        break;
+                unsigned long long klo = 0, khi = 0, h;
+                if (K > 0) {
+                    int g[K > 0 ? K : 1];
+#pragma unroll
+                    for (int i = 0; i < K; ++i) g[i] = win[i];
+#pragma unroll
+                    for (int i = K - 1; i >= 0; --i) {  // the first differing position decides
+                        const int f = g[i], cc = -g[K - 1 - i];
+                        if (f != cc) dir = f < cc ? 1 : -1;
+                    }
+                    if (packed && dir != 0) {
+                        const unsigned int bias = kb < 32 ? (1u << (kb - 1)) : 0u;
+                        unsigned long long lo = 0, hi = 0;
+#pragma unroll
+                        for (int i = 0; i < K; ++i) {
+                            const int cg = dir < 0 ? -g[K - 1 - i] : g[i];
+                            hi = (hi << kb) | (lo >> (64 - kb));
+                            lo = (lo << kb) | (unsigned long long)((unsigned int)cg + bias);
+                        }
+                        klo = lo & ((1ull << 62) - 1);
+                        khi = (hi << 2) | (lo >> 62);
+                    }
+                } else {
+                    for (int i = 0; i < k; ++i) {
+                        const int f = win[i], cc = -win[k - 1 - i];
+                        if (f != cc) {
+                            dir = f < cc ? 1 : -1;
+                            break;
+                        }
+                    }
+                    if (packed && dir != 0) {
+                        const unsigned int bias = kb < 32 ? (1u << (kb - 1)) : 0u;
+                        unsigned long long lo = 0, hi = 0;
+                        for (int i = 0; i < k; ++i) {
+                            const int cg = dir < 0 ? -win[k - 1 - i] : win[i];
+                            hi = (hi << kb) | (lo >> (64 - kb));
+                            lo = (lo << kb) | (unsigned long long)((unsigned int)cg + bias);
+                        }
+                        klo = lo & ((1ull << 62) - 1);
+                        khi = (hi << 2) | (lo >> 62);
                     }
                 }
                 if (dir == 0) {
                     P.status[ST_ERR] = AMIRA_E_PALINDROME;  // construct_gene_mer.py:23-25
                 } else {
                     const int dirneg = dir < 0;
-                    const unsigned long long h = canonical_hash(win, k, dirneg);
+                    h = packed ? packed_hash(klo, khi) : canonical_hash(win, k, dirneg);
                     const unsigned long long mine =
                         ((h >> FP_SHIFT) << FP_SHIFT) | ((unsigned long long)p << 1) | (unsigned long long)dirneg;
-                    const unsigned int slot = node_insert(P, win, dirneg, h, mine);
+                    const unsigned int slot = node_insert(P, win, dirneg, packed, klo, khi, h, mine);
                     val = slot | ((unsigned int)dirneg << 31);
                     if (!halo) {
                         atomicAdd(&P.ntab[slot].cov, 1u);
-                        const long long rs = (j <= NR_CAP) ? s_off[j] : P.off[r_lo + j];
-                        const long long wo = (j < NR_CAP) ? s_woff[j] : P.win_off[r_lo + j];
+                        const long long rs = (j <= NR_STAGE + 1) ? S.off[j] : P.off[r_lo + j];
+                        const long long wo = (j <= NR_STAGE) ? S.woff[j] : P.win_off[r_lo + j];
                         const int64_t w = wo + (p - rs);
                         P.win_node[w] = (int32_t)slot;
                         P.win_dir[w] = (int8_t)dir;
@@ -257,24 +376,25 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
                     }
                 }
             }
-            s_val[pl] = val;
+            S.val[pl] = val;
         }
-        __syncthreads();
+        __syncwarp();
         // ---- adjacent pairs of the same read
-        for (int pl = tid; pl < len; pl += INS_THREADS) {
-            const unsigned int a = s_val[pl], b = s_val[pl + 1];
+#pragma unroll 1
+        for (int pl = lane; pl < len; pl += 32) {
+            const unsigned int a = S.val[pl], b = S.val[pl + 1];
             if (a == INVALID_VAL || b == INVALID_VAL) continue;
-            if (pl + 1 < len && s_j[pl + 1] != s_j[pl]) continue;
+            if (pl + 1 < len && S.j[pl + 1] != S.j[pl]) continue;
             const unsigned int sa = a & 0x7FFFFFFFu, sb = b & 0x7FFFFFFFu;
             const unsigned int sdneg = a >> 31, tdneg = b >> 31;
             const unsigned int lo = min(sa, sb), hi = max(sa, sb);
             const unsigned long long key =
                 ((unsigned long long)lo << 32) | ((unsigned long long)hi << 1) | (unsigned long long)(sdneg == tdneg);
             const unsigned long long ord =
-                ((unsigned long long)(t0 + pl) << 2) | ((unsigned long long)(sa > sb) << 1) | sdneg;
+                ((unsigned long long)(c0 + pl) << 2) | ((unsigned long long)(sa > sb) << 1) | sdneg;
             edge_insert(P, key, ord);
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -361,15 +481,28 @@ __device__ __forceinline__ int uf_find(int32_t *parent, int x) {
     }
 }
 
+// Roots are linked by a hashed priority, not by index: first-seen node indices follow the reads, so
+// linking by index would build list-shaped trees (node i+1 under node i) and serialise every find.
+// Random linking keeps the expected depth logarithmic; the component's first node is recovered
+// afterwards with an atomicMin per root (k_cc_flatten).
+__device__ __forceinline__ unsigned int uf_prio(int x) {
+    unsigned int v = (unsigned int)x * 0x9E3779B1u;
+    v ^= v >> 15;
+    v *= 0x85EBCA77u;
+    v ^= v >> 13;
+    return v;
+}
+
 __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
     int ra = uf_find(parent, a), rb = uf_find(parent, b);
     while (ra != rb) {
-        if (ra < rb) {
+        const unsigned int pa = uf_prio(ra), pb = uf_prio(rb);
+        if (pa < pb || (pa == pb && ra < rb)) {
             int t = ra;
             ra = rb;
             rb = t;
         }
-        // hook the larger root under the smaller: the final root is the component's first node
+        // hook the root of higher priority value under the other one
         int old = atomicCAS(&parent[ra], ra, rb);
         if (old == ra) return;
         ra = uf_find(parent, old);
@@ -450,25 +583,33 @@ __global__ void k_adj_keys(const int32_t *__restrict__ e_src, const int8_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_cc_roots(int32_t *__restrict__ parent, int64_t n_nodes, int *__restrict__ is_root) {
+// root of every node (read-only walk: the unions are over, trees are shallow thanks to the random
+// linking) and each component's first node (cmin starts at 0xFFFFFFFF)
+__global__ void k_cc_flatten(const int32_t *__restrict__ parent, int64_t n_nodes, unsigned int *__restrict__ cmin,
+                             uint32_t *__restrict__ root) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) {
-        int r = uf_find(parent, (int)i);
-        parent[i] = r;
-        is_root[i] = (r == (int)i);
-    } else if (i == n_nodes) {
-        is_root[i] = 0;
-    }
+    if (i >= n_nodes) return;
+    int r = (int)i;
+    for (int p = parent[r]; p != r; p = parent[r]) r = p;
+    root[i] = (uint32_t)r;
+    // threads run roughly in index order: after the first few updates the minimum is final and the
+    // remaining nodes of a (giant) component skip the atomic
+    if ((unsigned int)i < ((volatile unsigned int *)cmin)[r]) atomicMin(&cmin[r], (unsigned int)i);
 }
 
-__global__ void k_cc_number(const int32_t *__restrict__ parent, const int *__restrict__ root_rank, int64_t n_nodes,
+__global__ void k_cc_first(const uint32_t *__restrict__ root, const unsigned int *__restrict__ cmin, int64_t n_nodes,
+                           int *__restrict__ is_first) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) is_first[i] = (cmin[root[i]] == (unsigned int)i);
+    else if (i == n_nodes) is_first[i] = 0;
+}
+
+// component ids 1, 2, ... in order of each component's first node (construct_graph.py:920-927);
+// comp holds the roots on entry
+__global__ void k_cc_number(const unsigned int *__restrict__ cmin, const int *__restrict__ first_rank, int64_t n_nodes,
                             uint32_t *__restrict__ comp) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) {
-        int r = parent[i];
-        r = parent[r];  // k_cc_roots flattened against a moving target; one more hop is enough
-        comp[i] = (uint32_t)root_rank[r] + 1u;
-    }
+    if (i < n_nodes) comp[i] = (uint32_t)first_rank[cmin[comp[i]]] + 1u;
 }
 
 // ---------------------------------------------------------------------------------------------

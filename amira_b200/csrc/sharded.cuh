@@ -102,7 +102,7 @@ __global__ void k_insert_records(const BuildParams P, long long n, const NodeRec
     const int32_t *win = P.ids + r * P.k;
     const unsigned long long h = canonical_hash(win, P.k, 0);
     const unsigned long long mine = ((h >> FP_SHIFT) << FP_SHIFT) | ((unsigned long long)(r * P.k) << 1);
-    const unsigned int slot = node_insert(P, win, 0, h, mine);
+    const unsigned int slot = node_insert(P, win, 0, false, 0ull, 0ull, h, mine);
     if (meta) atomicAdd(&P.ntab[slot].cov, meta[r].cov);
 }
 
