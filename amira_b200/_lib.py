@@ -6,20 +6,20 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libamira_gmg.so")
+LIB_PATH = os.environ.get("AMIRA_LIB_PATH", os.path.join(HERE, "libamira_gmg.so"))   # override: developer experiments
 
 OK = 0
 E_BLANK_GENE, E_BAD_STRAND, E_EMPTY_NAME, E_UNKNOWN_GENE, E_PALINDROME, E_EMPTY_GENEMER, E_MULTI_EDGE = 1, 2, 3, 4, 5, 6, 7
 E_ARG, E_STATE, E_CUDA, E_NOMEM, E_NCCL = 8, 9, 10, 11, 12
 PHASES = ("h2d", "windows", "insert", "order", "remap", "incidence", "adjacency", "components", "filter",
-          "exchange", "emit", "insert_kernel")
+          "exchange", "emit", "insert_kernel", "emit_nodes")
 
 EXPORTED = (
     "amira_last_error", "amira_version", "amira_vocab_encode", "amira_gmg_create", "amira_gmg_destroy",
     "amira_gmg_reserve", "amira_gmg_set_profiling", "amira_gmg_phase_ms", "amira_gmg_kernel_launches",
     "amira_gmg_build", "amira_gmg_sync", "amira_gmg_sizes", "amira_gmg_export_nodes", "amira_gmg_export_edges",
     "amira_gmg_export_reads", "amira_gmg_remove_low_coverage_components", "amira_gmg_filter",
-    "amira_gmg_filter_mask_sizes", "amira_gmg_export_filter_masks", "amira_gmg_nccl_unique_id", "amira_gmg_comm_init", "amira_gmg_atomic_peak",
+    "amira_gmg_filter_mask_sizes", "amira_gmg_export_filter_masks", "amira_gmg_nccl_unique_id", "amira_gmg_comm_init", "amira_gmg_atomic_peak", "amira_gmg_debug_layout",
 )
 
 _lib = None
@@ -61,7 +61,8 @@ def load():
     lib.amira_gmg_export_filter_masks.argtypes = [vp, vp, vp]
     lib.amira_gmg_nccl_unique_id.argtypes = [vp]
     lib.amira_gmg_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
-    lib.amira_gmg_atomic_peak.argtypes = [vp, i64, i64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.amira_gmg_debug_layout.argtypes = [vp, C.c_int]
+    lib.amira_gmg_atomic_peak.argtypes = [vp, i64, i64] + [C.POINTER(C.c_double)] * 3
     _lib = lib
     return lib
 

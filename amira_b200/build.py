@@ -26,7 +26,9 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    extra = os.environ.get("AMIRA_NVCC_FLAGS", "").split()       # developer experiments (e.g. -DAMIRA_INS_ILP=1)
+    out = os.environ.get("AMIRA_LIB_OUT", LIB)
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
           [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -34,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libamira_gmg.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

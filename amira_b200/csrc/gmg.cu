@@ -27,9 +27,20 @@ struct amira_gmg {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // Second stream: after the node order is known, (edges -> adjacency -> components) runs beside
+    // (per-read lists -> node/read incidence); `cur` / `cur_temp` are what the launch helpers use.
+    cudaStream_t stream2 = nullptr, cur = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DevBuf cub_temp2;
+    DevBuf *cur_temp = nullptr;
     int n_sm = 148;
     int insert_ctas_per_sm = 1;
-    int unpack_bits_failed = 0;  // widest packed-key width that did not fit this handle's gene ids
+    int force_layout = 0;        // test hook (amira_gmg_debug_layout): 1 = no 16-byte node slots, 2 = no 16-byte edge slots, 4 = no packed keys
+    int id_bits = 0;             // bits a signed gene id takes in a packed key (from the largest |id| seen); 0 = unknown
+    bool n16 = false, e16 = false;  // 16-byte node / edge slots in the current build
+    NodeView nview;
+    EdgeView eview;
+    DevBuf d_maxabs;
 
     // input (owned copy or borrowed device pointers)
     DevBuf d_ids, d_off, d_ps, d_pe;
@@ -94,18 +105,18 @@ struct Phase {
     int ph;
     Phase(amira_gmg *h_, int ph_) : h(h_), ph(ph_) {
         if (h->profiling) {
-            cudaEventRecord(h->ev[ph][0], h->stream);
+            cudaEventRecord(h->ev[ph][0], h->cur);
             h->ev_used[ph] = true;
         }
     }
     ~Phase() {
-        if (h->profiling) cudaEventRecord(h->ev[ph][1], h->stream);
+        if (h->profiling) cudaEventRecord(h->ev[ph][1], h->cur);
     }
 };
 
 #define LAUNCH(h, kern, grid, block, ...)                              \
     do {                                                               \
-        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);        \
+        kern<<<(grid), (block), 0, (h)->cur>>>(__VA_ARGS__);           \
         (h)->launches++;                                               \
         AMIRA_CUDA(cudaGetLastError());                                \
     } while (0)
@@ -114,16 +125,29 @@ template <typename F>
 int cub_call(amira_gmg *h, F f) {
     size_t bytes = 0;
     AMIRA_CUDA(f(nullptr, bytes));
-    AMIRA_TRY(h->cub_temp.reserve(bytes ? bytes : 1));
-    AMIRA_CUDA(f(h->cub_temp.p, bytes));
+    AMIRA_TRY(h->cur_temp->reserve(bytes ? bytes : 1));
+    AMIRA_CUDA(f(h->cur_temp->p, bytes));
     h->lib_launches++;
     return AMIRA_OK;
 }
 
 template <typename T>
 int exclusive_sum_inplace(amira_gmg *h, T *data, int64_t n) {
-    return cub_call(h, [&](void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum(t, b, data, data, n, h->stream); });
+    return cub_call(h, [&](void *t, size_t &b) { return cub::DeviceScan::ExclusiveSum(t, b, data, data, n, h->cur); });
 }
+
+// launches inside this scope go to the second stream (with its own CUB scratch)
+struct SideStream {
+    amira_gmg *h;
+    explicit SideStream(amira_gmg *h_) : h(h_) {
+        h->cur = h->stream2;
+        h->cur_temp = &h->cub_temp2;
+    }
+    ~SideStream() {
+        h->cur = h->stream;
+        h->cur_temp = &h->cub_temp;
+    }
+};
 
 int bits_for(int64_t n) {
     int b = 1;
@@ -150,7 +174,7 @@ int build_adjacency(amira_gmg *h) {
     Phase ph(h, AMIRA_PH_ADJACENCY);
     const int64_t N = h->n_nodes, E = h->n_edges;
     AMIRA_TRY(h->adj_off.reserve(sizeof(int64_t) * (2 * N + 2)));
-    AMIRA_CUDA(cudaMemsetAsync(h->adj_off.p, 0, sizeof(int64_t) * (2 * N + 2), h->stream));
+    AMIRA_CUDA(cudaMemsetAsync(h->adj_off.p, 0, sizeof(int64_t) * (2 * N + 2), h->cur));
     if (E > 0) {
         AMIRA_TRY(h->adj_keys.reserve(sizeof(uint32_t) * E));
         AMIRA_TRY(h->adj_keys2.reserve(sizeof(uint32_t) * E));
@@ -162,7 +186,7 @@ int build_adjacency(amira_gmg *h) {
         AMIRA_TRY(cub_call(h, [&](void *t, size_t &b) {
             return cub::DeviceRadixSort::SortPairs(t, b, h->adj_keys.as<uint32_t>(), h->adj_keys2.as<uint32_t>(),
                                                    h->adj_vals.as<int32_t>(), h->adj_edges.as<int32_t>(), E, 0, bits,
-                                                   h->stream);
+                                                   h->cur);
         }));
     }
     AMIRA_TRY(exclusive_sum_inplace(h, h->adj_off.as<int64_t>(), 2 * N + 1));
@@ -236,29 +260,58 @@ int do_build(amira_gmg *h) {
     if (h->hint_edges > 0) ecap = h->hint_edges * 2 + 1024;
     else if (h->prev_G > 0 && G <= 4 * h->prev_G)
         ecap = (int64_t)((double)h->prev_und_edges * ((double)G / (double)h->prev_G) * 2.0) + 4096;
-    // gene-mers of up to 124 bits are packed into the node slot: 124 / k bits per signed gene id.
-    // If an id does not fit (seen by the kernel while staging), the build is redone unpacked and the
-    // handle remembers the width that failed.
-    int key_bits = std::min(32, 124 / k);
-    if (key_bits < 8 || key_bits <= h->unpack_bits_failed) key_bits = 0;
+    int key_bits = 0;
+    bool n16 = false;
+    const bool e16 = G < (1ll << ORD32_P_BITS) && !(h->force_layout & 2);
     for (int attempt = 0;; ++attempt) {
+        // Layout of the node table: a gene takes id_bits bits in a packed key (the largest |id| of the
+        // input decides; remembered on the handle, checked by the insert kernel while it stages the
+        // ids).  k * id_bits <= 85: 16-byte slots whose identity is the key itself; <= 124: 32-byte
+        // slots with the key published next to the claim word; else gene-mers are compared through ids.
+        if (h->id_bits == 0 && G > 0) {
+            AMIRA_TRY(h->d_maxabs.reserve(sizeof(unsigned int)));
+            AMIRA_CUDA(cudaMemsetAsync(h->d_maxabs.p, 0, sizeof(unsigned int), st));
+            LAUNCH(h, k_max_abs, std::min<int>(grid_for(G, 256), h->n_sm * 16), 256, h->ids, G, h->d_maxabs.as<unsigned int>());
+            unsigned int max_abs = 0;
+            AMIRA_CUDA(cudaMemcpyAsync(&max_abs, h->d_maxabs.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            AMIRA_CUDA(cudaStreamSynchronize(st));
+            int b = 2;
+            while (b < 32 && ((1ull << (b - 1)) - 2) < (unsigned long long)max_abs) ++b;
+            h->id_bits = b;
+        }
+        const int T = k * (h->id_bits ? h->id_bits : 32);
+        n16 = T <= KEY16_BITS && h->id_bits < 32 && !(h->force_layout & 1);
+        key_bits = (T <= 124 && h->id_bits < 32 && !(h->force_layout & 4)) ? h->id_bits : 0;
+        h->n16 = n16;
+        h->e16 = e16;
         ncap = std::min<int64_t>(ncap, 0x7FFFFFF0ll);
         ecap = std::min<int64_t>(ecap, 0x7FFFFFF0ll);
         h->ncap = (unsigned int)ncap;
         h->ecap = (unsigned int)ecap;
-        AMIRA_TRY(h->ntab.reserve(sizeof(NodeSlot) * ncap));
-        AMIRA_TRY(h->etab.reserve(sizeof(EdgeSlot) * ecap));
+        const size_t nbytes = n16 ? (sizeof(NodeSlot16) + 2 * sizeof(unsigned int)) * (size_t)ncap : sizeof(NodeSlot) * (size_t)ncap;
+        const size_t ebytes = (e16 ? sizeof(EdgeSlot16) : sizeof(EdgeSlot)) * (size_t)ecap;
+        AMIRA_TRY(h->ntab.reserve(nbytes));
+        AMIRA_TRY(h->etab.reserve(ebytes));
+        if (n16) {  // [slots][coverage][node index]
+            unsigned int *side = reinterpret_cast<unsigned int *>(h->ntab.as<NodeSlot16>() + ncap);
+            h->nview = NodeView{h->ntab.as<unsigned long long>(), side, side + ncap, 2, 1, h->ncap};
+        } else {
+            unsigned int *u = h->ntab.as<unsigned int>();
+            h->nview = NodeView{h->ntab.as<unsigned long long>(), u + 2, u + 3, 4, 8, h->ncap};
+        }
+        h->eview = EdgeView{h->etab.p, h->ecap, e16 ? 1 : 0};
         {
             Phase ph(h, AMIRA_PH_INSERT);
-            AMIRA_CUDA(cudaMemsetAsync(h->ntab.p, 0xFF, sizeof(NodeSlot) * ncap, st));
-            AMIRA_CUDA(cudaMemsetAsync(h->etab.p, 0xFF, sizeof(EdgeSlot) * ecap, st));
+            AMIRA_CUDA(cudaMemsetAsync(h->ntab.p, 0xFF, nbytes, st));
+            AMIRA_CUDA(cudaMemsetAsync(h->etab.p, 0xFF, ebytes, st));
             h->lib_launches += 2;
             if (n_tiles > 0) {
                 BuildParams P;
                 P.ids = h->ids; P.off = h->off; P.win_off = h->win_off.as<int64_t>();
                 P.tile_r0 = h->tile_r0.as<int32_t>(); P.ps = h->ps; P.pe = h->pe;
                 P.G = G; P.R = R; P.n_tiles = n_tiles; P.k = k;
-                P.ntab = h->ntab.as<NodeSlot>(); P.ncap = h->ncap; P.etab = h->etab.as<EdgeSlot>(); P.ecap = h->ecap;
+                P.ntab = h->ntab.as<NodeSlot>(); P.ntab16 = h->ntab.as<NodeSlot16>(); P.ncov = h->nview.cov;
+                P.ncap = h->ncap; P.etab = h->etab.as<EdgeSlot>(); P.etab16 = h->etab.as<EdgeSlot16>(); P.ecap = h->ecap;
                 P.win_node = h->win_node.as<int32_t>(); P.win_dir = h->win_dir.as<int8_t>();
                 P.win_read = h->win_read.as<int32_t>();
                 P.win_start = h->has_pos ? h->win_start.as<int32_t>() : nullptr;
@@ -270,10 +323,20 @@ int do_build(amira_gmg *h) {
                 const int grid = (int)std::min<int64_t>((n_tiles + INS_WARPS - 1) / INS_WARPS,
                                                         (int64_t)h->n_sm * h->insert_ctas_per_sm);
                 Phase phk(h, AMIRA_PH_INSERT_KERNEL);
-                if (k == 3) LAUNCH(h, k_insert_windows<3>, grid, INS_THREADS, P);
-                else if (k == 5) LAUNCH(h, k_insert_windows<5>, grid, INS_THREADS, P);
-                else if (k == 7) LAUNCH(h, k_insert_windows<7>, grid, INS_THREADS, P);
-                else LAUNCH(h, k_insert_windows<0>, grid, INS_THREADS, P);
+#define INSERT_KE(KK, NN, EE) LAUNCH(h, (k_insert_windows<KK, NN, EE>), grid, INS_THREADS, P)
+#define INSERT_K(KK)                                  \
+    do {                                              \
+        if (n16 && e16) INSERT_KE(KK, true, true);    \
+        else if (n16) INSERT_KE(KK, true, false);     \
+        else if (e16) INSERT_KE(KK, false, true);     \
+        else INSERT_KE(KK, false, false);             \
+    } while (0)
+                if (k == 3) INSERT_K(3);
+                else if (k == 5) INSERT_K(5);
+                else if (k == 7) INSERT_K(7);
+                else INSERT_K(0);
+#undef INSERT_K
+#undef INSERT_KE
             }
         }
         if (h->world > 1) {
@@ -282,8 +345,8 @@ int do_build(amira_gmg *h) {
             Phase ph(h, AMIRA_PH_ORDER);
             AMIRA_CUDA(cudaMemsetAsync(h->bitmaps.p, 0, sizeof(unsigned int) * 3 * (n_words + 1), st));
             const unsigned int tmax = std::max(h->ncap, h->ecap);
-            LAUNCH(h, k_mark_first, std::min<int>(grid_for(tmax, 256), h->n_sm * 16), 256, h->ntab.as<NodeSlot>(), h->ncap,
-                   h->etab.as<EdgeSlot>(), h->ecap, bm_node, bm_ea, bm_eb);
+            LAUNCH(h, k_mark_first, std::min<int>(grid_for(tmax, 256), h->n_sm * 16), 256, h->nview, h->eview, bm_node, bm_ea,
+                   bm_eb);
             LAUNCH(h, k_popcount, grid_for(n_words + 1, 256), 256, bm_node, bm_ea, bm_eb, n_words, h->cnt_node.as<int>(),
                    h->cnt_edge.as<int>());
             AMIRA_TRY(exclusive_sum_inplace(h, h->cnt_node.as<int>(), n_words + 1));
@@ -295,10 +358,7 @@ int do_build(amira_gmg *h) {
         if (h->h_status[ST_ERR]) break;
         const bool ovn = h->h_status[ST_OVERFLOW_N], ove = h->h_status[ST_OVERFLOW_E];
         const bool unpack = h->h_status[ST_UNPACK] && key_bits > 0;
-        if (unpack) {
-            h->unpack_bits_failed = std::max(h->unpack_bits_failed, key_bits);
-            key_bits = 0;
-        }
+        if (unpack) h->id_bits = 0;  // an id outgrew the remembered width: measure again
         if (!ovn && !ove && !unpack) break;
         if (attempt >= 6) {
             set_error("hash tables overflowed after %d attempts (ncap=%lld ecap=%lld)", attempt + 1, (long long)ncap,
@@ -339,49 +399,72 @@ int do_build(amira_gmg *h) {
     }
     const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
 
-    // ---- node / edge arrays in first-seen order, union-find on the way
+    // ---- node arrays in first-seen order (both branches below need the node indices)
     if (h->world == 1) {
-        Phase ph(h, AMIRA_PH_EMIT);
+        Phase ph(h, AMIRA_PH_EMIT_NODES);
         AMIRA_TRY(h->node_key.reserve(sizeof(int32_t) * std::max<int64_t>(1, N * k)));
         AMIRA_TRY(h->node_cov.reserve(sizeof(uint32_t) * (N + 1)));
         AMIRA_TRY(h->node_dir.reserve(N + 1));
         AMIRA_TRY(h->node_comp.reserve(sizeof(uint32_t) * (N + 1)));
         AMIRA_TRY(h->parent.reserve(sizeof(int32_t) * (N + 1)));
         AMIRA_TRY(h->is_root.reserve(sizeof(int) * (N + 2)));
-        AMIRA_TRY(h->e_src.reserve(sizeof(int32_t) * (E + 1)));
-        AMIRA_TRY(h->e_tgt.reserve(sizeof(int32_t) * (E + 1)));
-        AMIRA_TRY(h->e_sd.reserve(E + 1));
-        AMIRA_TRY(h->e_td.reserve(E + 1));
-        AMIRA_TRY(h->e_cov.reserve(sizeof(uint32_t) * (E + 1)));
         if (N > 0) {
-            LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->ntab.as<NodeSlot>(), h->ncap,
-                   h->ids, k, bm_node, h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
+            LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->nview, h->ids, k, bm_node,
+                   h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
                    h->node_dir.as<int8_t>(), h->parent.as<int32_t>());
         }
-        if (E > 0) {
-            LAUNCH(h, k_emit_edges, std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16), 256, h->etab.as<EdgeSlot>(), h->ecap,
-                   h->ntab.as<NodeSlot>(), bm_ea, bm_eb, h->cnt_edge.as<int>(), h->e_src.as<int32_t>(),
-                   h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(), h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(),
-                   h->parent.as<int32_t>());
-        }
     }
-    // ---- per-read node lists: slot -> node index
+    // reserve everything the two branches touch before forking (a growing buffer synchronises the device)
+    AMIRA_TRY(h->e_src.reserve(sizeof(int32_t) * (E + 1)));
+    AMIRA_TRY(h->e_tgt.reserve(sizeof(int32_t) * (E + 1)));
+    AMIRA_TRY(h->e_sd.reserve(E + 1));
+    AMIRA_TRY(h->e_td.reserve(E + 1));
+    AMIRA_TRY(h->e_cov.reserve(sizeof(uint32_t) * (E + 1)));
+    AMIRA_TRY(h->cc_min.reserve(sizeof(unsigned int) * (N + 1)));
+    AMIRA_TRY(h->reads_off.reserve(sizeof(int64_t) * (N + 2)));
+    AMIRA_TRY(h->reads.reserve(sizeof(int32_t) * std::max<int64_t>(1, W)));
+    AMIRA_TRY(h->dups.reserve(sizeof(uint32_t) * (N + 1)));
+    if (W > 0) {
+        AMIRA_TRY(h->sort_keys.reserve(sizeof(int32_t) * W));
+        AMIRA_TRY(h->sort_vals.reserve(sizeof(int32_t) * W));
+        AMIRA_TRY(h->flags.reserve(W));
+    }
+    AMIRA_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    AMIRA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    // ---- branch B (second stream): edges in first-seen order + union-find, adjacency, components
+    {
+        SideStream side(h);
+        if (h->world == 1 && E > 0) {
+            Phase ph(h, AMIRA_PH_EMIT);
+            LAUNCH(h, k_emit_edges, std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16), 256, h->eview, h->nview, bm_ea, bm_eb,
+                   h->cnt_edge.as<int>(), h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
+                   h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->parent.as<int32_t>());
+        }
+        AMIRA_TRY(build_adjacency(h));
+        {
+            Phase ph(h, AMIRA_PH_COMPONENTS);
+            AMIRA_CUDA(cudaMemsetAsync(h->cc_min.p, 0xFF, sizeof(unsigned int) * (N + 1), h->cur));
+            if (N > 0)
+                LAUNCH(h, k_cc_flatten, grid_for(N, 256), 256, h->parent.as<int32_t>(), N, h->cc_min.as<unsigned int>(),
+                       h->node_comp.as<uint32_t>());
+            LAUNCH(h, k_cc_first, grid_for(N + 1, 256), 256, h->node_comp.as<uint32_t>(), h->cc_min.as<unsigned int>(), N,
+                   h->is_root.as<int>());
+            AMIRA_TRY(exclusive_sum_inplace(h, h->is_root.as<int>(), N + 1));
+            if (N > 0)
+                LAUNCH(h, k_cc_number, grid_for(N, 256), 256, h->cc_min.as<unsigned int>(), h->is_root.as<int>(), N,
+                       h->node_comp.as<uint32_t>());
+        }
+        AMIRA_CUDA(cudaEventRecord(h->ev_join, h->cur));
+    }
+    // ---- branch A (main stream): per-read node lists (slot -> node index), then node -> reads
     if (W > 0) {
         Phase ph(h, AMIRA_PH_REMAP);
-        LAUNCH(h, k_remap_windows, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->ntab.as<NodeSlot>(),
-               h->win_node.as<int32_t>(), W);
+        LAUNCH(h, k_remap_windows, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->nview, h->win_node.as<int32_t>(), W);
     }
-    // ---- node -> reads
     {
         Phase ph(h, AMIRA_PH_INCIDENCE);
-        AMIRA_TRY(h->reads_off.reserve(sizeof(int64_t) * (N + 2)));
-        AMIRA_TRY(h->reads.reserve(sizeof(int32_t) * std::max<int64_t>(1, W)));
-        AMIRA_TRY(h->dups.reserve(sizeof(uint32_t) * (N + 1)));
         AMIRA_CUDA(cudaMemsetAsync(h->dups.p, 0, sizeof(uint32_t) * (N + 1), st));
         if (W > 0) {
-            AMIRA_TRY(h->sort_keys.reserve(sizeof(int32_t) * W));
-            AMIRA_TRY(h->sort_vals.reserve(sizeof(int32_t) * W));
-            AMIRA_TRY(h->flags.reserve(W));
             const int bits = bits_for(N);
             AMIRA_TRY(cub_call(h, [&](void *t, size_t &b) {
                 return cub::DeviceRadixSort::SortPairs(t, b, h->win_node.as<uint32_t>(), h->sort_keys.as<uint32_t>(),
@@ -402,22 +485,7 @@ int do_build(amira_gmg *h) {
                h->reads_off.as<int64_t>());
         AMIRA_TRY(exclusive_sum_inplace(h, h->reads_off.as<int64_t>(), N + 1));
     }
-    AMIRA_TRY(build_adjacency(h));
-    // ---- components
-    {
-        Phase ph(h, AMIRA_PH_COMPONENTS);
-        AMIRA_TRY(h->cc_min.reserve(sizeof(unsigned int) * (N + 1)));
-        AMIRA_CUDA(cudaMemsetAsync(h->cc_min.p, 0xFF, sizeof(unsigned int) * (N + 1), st));
-        if (N > 0)
-            LAUNCH(h, k_cc_flatten, grid_for(N, 256), 256, h->parent.as<int32_t>(), N, h->cc_min.as<unsigned int>(),
-                   h->node_comp.as<uint32_t>());
-        LAUNCH(h, k_cc_first, grid_for(N + 1, 256), 256, h->node_comp.as<uint32_t>(), h->cc_min.as<unsigned int>(), N,
-               h->is_root.as<int>());
-        AMIRA_TRY(exclusive_sum_inplace(h, h->is_root.as<int>(), N + 1));
-        if (N > 0)
-            LAUNCH(h, k_cc_number, grid_for(N, 256), 256, h->cc_min.as<unsigned int>(), h->is_root.as<int>(), N,
-                   h->node_comp.as<uint32_t>());
-    }
+    AMIRA_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->n_comps = N;  // upper bound on component ids (ids are <= number of nodes)
     h->sizes_dirty = true;
     return AMIRA_OK;
@@ -583,8 +651,7 @@ int sharded_merge(amira_gmg *h) {
 
     // ---- nodes: route one record per locally-unique gene-mer to its owner
     AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, st));
-    LAUNCH(h, k_node_route<false>, tgrid_n, 256, h->ntab.as<NodeSlot>(), h->ncap, h->ids, k, world, call_base, d_cnt,
-           nullptr, nullptr, nullptr);
+    LAUNCH(h, k_node_route<false>, tgrid_n, 256, h->nview, h->ids, k, world, call_base, d_cnt, nullptr, nullptr, nullptr);
     AMIRA_TRY(exchange_counts(h, send_off, recv_off));
     const int64_t Nl = send_off[world], Nr = recv_off[world];
     AMIRA_TRY(h->x_skey.reserve(key_bytes * std::max<int64_t>(Nl, 1)));
@@ -593,7 +660,7 @@ int sharded_merge(amira_gmg *h) {
     AMIRA_TRY(h->x_rmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
     AMIRA_TRY(h->x_rkey2.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
     AMIRA_TRY(h->x_rmeta2.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
-    LAUNCH(h, k_node_route<true>, tgrid_n, 256, h->ntab.as<NodeSlot>(), h->ncap, h->ids, k, world, call_base, d_cnt, d_off,
+    LAUNCH(h, k_node_route<true>, tgrid_n, 256, h->nview, h->ids, k, world, call_base, d_cnt, d_off,
            h->x_skey.as<int32_t>(), h->x_smeta.as<NodeRec>());
     AMIRA_TRY(comm_alltoallv(h->comm, h->x_skey.p, send_off.data(), h->x_rkey.p, recv_off.data(), key_bytes, st));
     AMIRA_TRY(comm_alltoallv(h->comm, h->x_smeta.p, send_off.data(), h->x_rmeta.p, recv_off.data(), sizeof(NodeRec), st));
@@ -667,21 +734,19 @@ int sharded_merge(amira_gmg *h) {
         P.ntab = h->x_tab.as<NodeSlot>();
         P.ncap = (unsigned int)mcap;
         LAUNCH(h, k_insert_records, grid_for(Ng, 256), 256, P, (long long)Ng, nullptr);
-        LAUNCH(h, k_local_to_global, tgrid_n, 256, h->ntab.as<NodeSlot>(), h->ncap, h->x_skey.as<int32_t>(), P,
-               h->cov_local.as<uint32_t>());
+        LAUNCH(h, k_local_to_global, tgrid_n, 256, h->nview, h->x_skey.as<int32_t>(), P, h->cov_local.as<uint32_t>());
     }
 
     // ---- edges: one record per locally-unique undirected adjacency, keyed on global node indices
     AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, st));
-    LAUNCH(h, k_edge_route<false>, tgrid_e, 256, h->etab.as<EdgeSlot>(), h->ecap, h->ntab.as<NodeSlot>(), world, call_base,
-           d_cnt, nullptr, nullptr);
+    LAUNCH(h, k_edge_route<false>, tgrid_e, 256, h->eview, h->nview, world, call_base, d_cnt, nullptr, nullptr);
     AMIRA_TRY(exchange_counts(h, send_off, recv_off));
     const int64_t El = send_off[world], Er = recv_off[world];
     AMIRA_TRY(h->x_sedge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(El, 1)));
     AMIRA_TRY(h->x_redge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Er, 1)));
     AMIRA_TRY(h->x_medge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Er, 1)));
-    LAUNCH(h, k_edge_route<true>, tgrid_e, 256, h->etab.as<EdgeSlot>(), h->ecap, h->ntab.as<NodeSlot>(), world, call_base,
-           d_cnt, d_off, h->x_sedge.as<EdgeSlot>());
+    LAUNCH(h, k_edge_route<true>, tgrid_e, 256, h->eview, h->nview, world, call_base, d_cnt, d_off,
+           h->x_sedge.as<EdgeSlot>());
     AMIRA_TRY(comm_alltoallv(h->comm, h->x_sedge.p, send_off.data(), h->x_redge.p, recv_off.data(), sizeof(EdgeSlot), st));
     const int64_t mecap = std::min<int64_t>(2 * Er + 1024, 0x7FFFFFF0ll);
     AMIRA_TRY(h->x_etab.reserve(sizeof(EdgeSlot) * mecap));
@@ -793,11 +858,22 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
         AMIRA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
     }
+    {
+        // high priority: the second stream carries many small, latency-bound kernels that should slip in
+        // between the waves of the bandwidth-bound sort on the main stream
+        int prio_lo = 0, prio_hi = 0;
+        AMIRA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        AMIRA_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi));
+    }
+    AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    h->cur = h->stream;
+    h->cur_temp = &h->cub_temp;
     cudaDeviceProp prop;
     AMIRA_CUDA(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
     int occ = 1;
-    AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_insert_windows<5>, INS_THREADS, 0));
+    AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_insert_windows<5, true, true>), INS_THREADS, 0));
     h->insert_ctas_per_sm = std::max(1, occ);
     AMIRA_TRY(h->d_status.reserve(sizeof(int) * ST_COUNT));
     AMIRA_TRY(h->d_sizes.reserve(sizeof(long long) * SZ_COUNT));
@@ -814,6 +890,13 @@ void amira_gmg_destroy(amira_gmg *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->stream2) {
+        cudaStreamSynchronize(h->stream2);
+        cudaStreamDestroy(h->stream2);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    h->cub_temp2.release();
     DevBuf *bufs[] = {&h->d_ids, &h->d_off, &h->d_ps, &h->d_pe, &h->win_off, &h->is_short, &h->to_correct, &h->tile_r0,
                       &h->win_node, &h->win_dir, &h->win_read, &h->win_start, &h->win_end, &h->ntab, &h->etab,
                       &h->bitmaps, &h->cnt_node, &h->cnt_edge, &h->node_key, &h->node_cov, &h->node_dir, &h->node_comp,
@@ -825,7 +908,7 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->d_nsel, &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rkey2, &h->x_rmeta2,
                       &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_sortk, &h->x_sortk2, &h->x_sorti,
                       &h->x_sorti2, &h->x_sedge, &h->x_redge, &h->x_medge, &h->x_gedge, &h->x_etab, &h->x_fan,
-                      &h->cov_local, &h->cc_min};
+                      &h->cov_local, &h->cc_min, &h->d_maxabs};
     for (DevBuf *b : bufs) b->release();
     if (h->comm) comm_destroy(h->comm);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -1114,6 +1197,12 @@ int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edg
     return AMIRA_OK;
 }
 
+int amira_gmg_debug_layout(amira_gmg *h, int mask) {
+    AMIRA_TRY(check_handle(h));
+    h->force_layout = mask;
+    return AMIRA_OK;
+}
+
 int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int world) {
     AMIRA_TRY(check_handle(h));
     if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world || !nccl_unique_id) {
@@ -1134,7 +1223,8 @@ int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int 
     return AMIRA_OK;
 }
 
-int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, double *red_add_per_s, double *cas_per_s) {
+int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, double *red_add_per_s, double *cas_per_s,
+                          double *load_per_s) {
     AMIRA_TRY(check_handle(h));
     if (table_bytes < 64 || n_ops < 1) return AMIRA_E_ARG;
     DevBuf t;
@@ -1144,7 +1234,8 @@ int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, doub
     AMIRA_CUDA(cudaEventCreate(&b));
     const int grid = h->n_sm * 8;
     float ms = 0.f;
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < 3; ++which) {
+        if (which == 2 && !load_per_s) break;
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
             AMIRA_CUDA(cudaMemsetAsync(t.p, 0xFF, (size_t)table_bytes, h->stream));
@@ -1152,9 +1243,12 @@ int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, doub
             if (which == 0)
                 LAUNCH(h, k_atomic_red, grid, 256, t.as<unsigned int>(), (unsigned long long)(table_bytes / 4),
                        (unsigned long long)n_ops, 0x1234ull + rep);
-            else
+            else if (which == 1)
                 LAUNCH(h, k_atomic_cas, grid, 256, t.as<unsigned long long>(), (unsigned long long)(table_bytes / 8),
                        (unsigned long long)n_ops, 0x1234ull + rep);
+            else
+                LAUNCH(h, k_random_load, grid, 256, t.as<NodeSlot>(), (unsigned long long)(table_bytes / 32),
+                       (unsigned long long)n_ops, 0x1234ull + rep, (unsigned long long *)h->d_nsel.p);
             AMIRA_CUDA(cudaEventRecord(b, h->stream));
             AMIRA_CUDA(cudaEventSynchronize(b));
             AMIRA_CUDA(cudaEventElapsedTime(&ms, a, b));
@@ -1163,6 +1257,7 @@ int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, doub
         double rate = (double)n_ops / (best * 1e-3);
         if (which == 0 && red_add_per_s) *red_add_per_s = rate;
         if (which == 1 && cas_per_s) *cas_per_s = rate;
+        if (which == 2 && load_per_s) *load_per_s = rate;
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);

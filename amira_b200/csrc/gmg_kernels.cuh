@@ -52,9 +52,12 @@ struct BuildParams {
     const int32_t *pe;
     int64_t G, R, n_tiles;
     int k;
-    NodeSlot *ntab;
+    NodeSlot *ntab;      // 32-byte node slots (or NodeSlot16 *ntab16 + ncov when the gene-mers fit 85 bits)
+    NodeSlot16 *ntab16;
+    unsigned int *ncov;  // coverage side array of the 16-byte layout (counts from 0xFFFFFFFF)
     unsigned int ncap;
-    EdgeSlot *etab;
+    EdgeSlot *etab;      // 32-byte edge slots (or EdgeSlot16 *etab16 when call positions fit 30 bits)
+    EdgeSlot16 *etab16;
     unsigned int ecap;
     int32_t *win_node;
     int8_t *win_dir;
@@ -63,7 +66,7 @@ struct BuildParams {
     int32_t *win_end;
     int *status;
     int64_t read_base;  // global index of this shard's first read (multi-GPU)
-    int key_bits;       // bits per gene of the packed 124-bit key; 0: gene-mers are compared through ids
+    int key_bits;       // bits per gene of the packed key (<= 124 bits); 0: gene-mers are compared through ids
     int ids_aligned;    // ids is 16-byte aligned (128-bit staging loads)
 };
 
@@ -150,7 +153,7 @@ __device__ __forceinline__ bool same_as_representative(const BuildParams &P, con
 }
 
 // Node table insert-or-find.  The slot is claimed by a CAS on `word` (fingerprint | first call
-// position | first direction); the winner then publishes the packed 124-bit key in the same 32-byte
+// position | first direction); the winner then publishes the packed key (<= 124 bits) in the same 32-byte
 // sector, so that every later visitor decides "same gene-mer?" from the one sector it loaded.
 // Until the key is published (or when the gene-mer does not fit 124 bits: packed == false) the
 // comparison falls back to the representative window ids[p .. p+k) named by `word`.
@@ -210,6 +213,69 @@ __device__ __forceinline__ void edge_insert(const BuildParams &P, unsigned long 
     P.status[ST_OVERFLOW_E] = 1;
 }
 
+// ---- 16-byte layouts (see common.cuh) -------------------------------------------------------------
+__device__ __forceinline__ void load_slot16(const void *s, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(s));
+}
+
+// mine = (top 22 key bits) << 42 | first position << 1 | first direction; keylow = low 63 key bits
+__device__ __forceinline__ unsigned int node_insert16(const BuildParams &P, const int32_t *win, int dirneg,
+                                                      unsigned long long keylow, unsigned long long h,
+                                                      unsigned long long mine) {
+    const unsigned int cap = P.ncap;
+    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
+    const unsigned int top = (unsigned int)(mine >> FP_SHIFT);
+    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+        unsigned long long cur, key;
+        load_slot16(&P.ntab16[s], cur, key);
+        if (cur == EMPTY64) {
+            unsigned long long old = atomicCAS(&P.ntab16[s].word, EMPTY64, mine);
+            if (old == EMPTY64) {
+                __stcg(&P.ntab16[s].key, keylow);
+                return s;
+            }
+            cur = old;
+            key = EMPTY64;
+        }
+        if ((unsigned int)(cur >> FP_SHIFT) == top) {
+            const bool same = (key != EMPTY64) ? (key == keylow) : same_as_representative(P, win, dirneg, cur);
+            if (same) {
+                if (mine < cur) atomicMin(&P.ntab16[s].word, mine);  // keep the first occurrence
+                return s;
+            }
+        }
+        if (++s == cap) s = 0;
+    }
+    P.status[ST_OVERFLOW_N] = 1;
+    return 0;
+}
+
+__device__ __forceinline__ void edge_insert16(const BuildParams &P, unsigned long long key, unsigned int ord) {
+    const unsigned int cap = P.ecap;
+    unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ULL;
+    unsigned int s = (unsigned int)(h >> 32);
+    s = (unsigned int)(((unsigned long long)s * cap) >> 32);
+    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+        unsigned long long cur, co;
+        load_slot16(&P.etab16[s], cur, co);
+        unsigned int cord = (unsigned int)(co >> 32);
+        if (cur == EMPTY64) {
+            unsigned long long old = atomicCAS(&P.etab16[s].key, EMPTY64, key);
+            cur = (old == EMPTY64) ? key : old;
+            cord = 0xFFFFFFFFu;
+        }
+        if (cur == key) {
+            if (ord < cord) atomicMin(&P.etab16[s].ord, ord);
+            atomicAdd(&P.etab16[s].cov, 1u);
+            return;
+        }
+        if (++s == cap) s = 0;
+    }
+    P.status[ST_OVERFLOW_E] = 1;
+}
+
 // per-warp staging area: one 128-call chunk (+ halo) and what the lanes exchange about it
 struct __align__(16) WarpStage {
     int32_t ids[WC + MAX_K + 4];
@@ -224,13 +290,14 @@ struct __align__(16) WarpStage {
 // starts that fall in the chunk, canonicalises / packs / hashes each window, inserts into the node
 // table, writes the per-window outputs, and inserts the adjacent-pair edges from the slot numbers
 // it staged in shared memory.  K > 0: gene-mer size known at compile time (windows in registers).
-template <int K>
+// N16 / E16: 16-byte node / edge slots.
+template <int K, bool N16, bool E16>
 __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParams P) {
     __shared__ WarpStage s_stage[INS_WARPS];
     const int lane = threadIdx.x & 31;
     WarpStage &S = s_stage[threadIdx.x >> 5];
     const int k = K ? K : P.k;
-    const int kb = P.key_bits;
+    const int kb = P.key_bits;  // bits per gene of the packed key (from the largest |id|), 0 = unpacked
     const bool packed = kb > 0;
     const int64_t n_warps = (int64_t)gridDim.x * INS_WARPS;
     for (int64_t c = (int64_t)blockIdx.x * INS_WARPS + (threadIdx.x >> 5); c < P.n_tiles; c += n_warps) {
@@ -244,29 +311,28 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
         // ---- stage the chunk (+ halo); c0 is a multiple of 128 calls
         {
             const int32_t *src = P.ids + c0;
+            // an id must leave the all-ones field value free: an all-ones key half means "not published"
+            const unsigned int bias = packed ? (1u << (kb - 1)) : 0u, lim = packed ? ((1u << kb) - 1u) : 0xFFFFFFFFu;
             bool bad = false;
             const int i4 = lane * 4;
             if (P.ids_aligned && i4 + 4 <= n_load) {
-                const int4 v = __ldg(reinterpret_cast<const int4 *>(src) + lane);
+                const int4 v = __ldcs(reinterpret_cast<const int4 *>(src) + lane);  // streamed once: evict first
                 *reinterpret_cast<int4 *>(&S.ids[i4]) = v;
-                if (packed && kb < 32) {
-                    const unsigned int bias = 1u << (kb - 1), lim = 1u << kb;
-                    bad = ((unsigned int)v.x + bias >= lim) | ((unsigned int)v.y + bias >= lim) |
-                          ((unsigned int)v.z + bias >= lim) | ((unsigned int)v.w + bias >= lim);
-                }
+                bad = ((unsigned int)v.x + bias >= lim) | ((unsigned int)v.y + bias >= lim) |
+                      ((unsigned int)v.z + bias >= lim) | ((unsigned int)v.w + bias >= lim);
             } else {
                 for (int i = i4; i < i4 + 4 && i < n_load; ++i) {
-                    const int g = __ldg(src + i);
+                    const int g = __ldcs(src + i);
                     S.ids[i] = g;
-                    if (packed && kb < 32) bad |= ((unsigned int)g + (1u << (kb - 1)) >= (1u << kb));
+                    bad |= ((unsigned int)g + bias >= lim);
                 }
             }
             for (int i = WC + lane; i < n_load; i += 32) {
-                const int g = __ldg(src + i);
+                const int g = __ldcs(src + i);
                 S.ids[i] = g;
-                if (packed && kb < 32) bad |= ((unsigned int)g + (1u << (kb - 1)) >= (1u << kb));
+                bad |= ((unsigned int)g + bias >= lim);
             }
-            if (bad) P.status[ST_UNPACK] = 1;  // an id does not fit the packed key: the host retries unpacked
+            if (packed && bad) P.status[ST_UNPACK] = 1;  // the host redoes the build unpacked
         }
         *reinterpret_cast<int4 *>(&S.j[lane * 4]) = make_int4(0, 0, 0, 0);
         for (int i = lane; i <= nr && i <= NR_STAGE + 1; i += 32) S.off[i] = P.off[r_lo + i];
@@ -315,22 +381,21 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
                     int g[K > 0 ? K : 1];
 #pragma unroll
                     for (int i = 0; i < K; ++i) g[i] = win[i];
+                    // window vs reverse complement, lexicographically: position i compares g[i] with
+                    // -g[K-1-i]; positions past the middle repeat the first half's tests mirrored
 #pragma unroll
-                    for (int i = K - 1; i >= 0; --i) {  // the first differing position decides
+                    for (int i = (K - 1) / 2; i >= 0; --i) {  // the first differing position decides
                         const int f = g[i], cc = -g[K - 1 - i];
                         if (f != cc) dir = f < cc ? 1 : -1;
                     }
                     if (packed && dir != 0) {
-                        const unsigned int bias = kb < 32 ? (1u << (kb - 1)) : 0u;
-                        unsigned long long lo = 0, hi = 0;
+                        const unsigned int bias = 1u << (kb - 1);
 #pragma unroll
                         for (int i = 0; i < K; ++i) {
                             const int cg = dir < 0 ? -g[K - 1 - i] : g[i];
-                            hi = (hi << kb) | (lo >> (64 - kb));
-                            lo = (lo << kb) | (unsigned long long)((unsigned int)cg + bias);
+                            khi = (khi << kb) | (klo >> (64 - kb));
+                            klo = (klo << kb) | (unsigned long long)((unsigned int)cg + bias);
                         }
-                        klo = lo & ((1ull << 62) - 1);
-                        khi = (hi << 2) | (lo >> 62);
                     }
                 } else {
                     for (int i = 0; i < k; ++i) {
@@ -341,15 +406,12 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
                         }
                     }
                     if (packed && dir != 0) {
-                        const unsigned int bias = kb < 32 ? (1u << (kb - 1)) : 0u;
-                        unsigned long long lo = 0, hi = 0;
+                        const unsigned int bias = 1u << (kb - 1);
                         for (int i = 0; i < k; ++i) {
                             const int cg = dir < 0 ? -win[k - 1 - i] : win[i];
-                            hi = (hi << kb) | (lo >> (64 - kb));
-                            lo = (lo << kb) | (unsigned long long)((unsigned int)cg + bias);
+                            khi = (khi << kb) | (klo >> (64 - kb));
+                            klo = (klo << kb) | (unsigned long long)((unsigned int)cg + bias);
                         }
-                        klo = lo & ((1ull << 62) - 1);
-                        khi = (hi << 2) | (lo >> 62);
                     }
                 }
                 if (dir == 0) {
@@ -357,18 +419,27 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
                 } else {
                     const int dirneg = dir < 0;
                     h = packed ? packed_hash(klo, khi) : canonical_hash(win, k, dirneg);
-                    const unsigned long long mine =
-                        ((h >> FP_SHIFT) << FP_SHIFT) | ((unsigned long long)p << 1) | (unsigned long long)dirneg;
-                    const unsigned int slot = node_insert(P, win, dirneg, packed, klo, khi, h, mine);
+                    unsigned int slot;
+                    if (N16) {
+                        // the key's bits 63..84 take the place of the fingerprint
+                        const unsigned long long top = (khi << 1) | (klo >> 63);
+                        const unsigned long long mine =
+                            (top << FP_SHIFT) | ((unsigned long long)p << 1) | (unsigned long long)dirneg;
+                        slot = node_insert16(P, win, dirneg, klo & 0x7FFFFFFFFFFFFFFFull, h, mine);
+                    } else {
+                        const unsigned long long mine =
+                            ((h >> FP_SHIFT) << FP_SHIFT) | ((unsigned long long)p << 1) | (unsigned long long)dirneg;
+                        slot = node_insert(P, win, dirneg, packed, klo, khi, h, mine);
+                    }
                     val = slot | ((unsigned int)dirneg << 31);
                     if (!halo) {
-                        atomicAdd(&P.ntab[slot].cov, 1u);
+                        atomicAdd(N16 ? &P.ncov[slot] : &P.ntab[slot].cov, 1u);
                         const long long rs = (j <= NR_STAGE + 1) ? S.off[j] : P.off[r_lo + j];
                         const long long wo = (j <= NR_STAGE) ? S.woff[j] : P.win_off[r_lo + j];
                         const int64_t w = wo + (p - rs);
-                        P.win_node[w] = (int32_t)slot;
-                        P.win_dir[w] = (int8_t)dir;
-                        P.win_read[w] = (int32_t)(r_lo + j);
+                        __stcs(&P.win_node[w], (int32_t)slot);  // streaming stores: keep the tables in L2
+                        __stcs(&P.win_dir[w], (signed char)dir);
+                        __stcs(&P.win_read[w], (int32_t)(r_lo + j));
                         if (P.ps) {
                             P.win_start[w] = __ldg(P.ps + p);
                             P.win_end[w] = __ldg(P.pe + p + k - 1);
@@ -392,7 +463,8 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
                 ((unsigned long long)lo << 32) | ((unsigned long long)hi << 1) | (unsigned long long)(sdneg == tdneg);
             const unsigned long long ord =
                 ((unsigned long long)(c0 + pl) << 2) | ((unsigned long long)(sa > sb) << 1) | sdneg;
-            edge_insert(P, key, ord);
+            if (E16) edge_insert16(P, key, (unsigned int)ord);
+            else edge_insert(P, key, ord);
         }
         __syncwarp();
     }
@@ -402,24 +474,24 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
 // first-seen order: bit p of bm_node is set iff a node was first seen at call p; bm_ea likewise for
 // undirected edge entries (first pair at p), bm_eb additionally when the entry is not a self-edge
 // (it then expands to two directed edges).
-__global__ void k_mark_first(const NodeSlot *__restrict__ ntab, unsigned int ncap,
-                             const EdgeSlot *__restrict__ etab, unsigned int ecap,
-                             unsigned int *__restrict__ bm_node, unsigned int *__restrict__ bm_ea,
-                             unsigned int *__restrict__ bm_eb) {
+__global__ void k_mark_first(const NodeView nv, const EdgeView ev, unsigned int *__restrict__ bm_node,
+                             unsigned int *__restrict__ bm_ea, unsigned int *__restrict__ bm_eb) {
     const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int ncap = nv.cap, ecap = ev.cap;
     const unsigned int n = max(ncap, ecap);
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
         if (s < ncap) {
-            unsigned long long w = ntab[s].word;
+            unsigned long long w = nv.w(s);
             if (w != EMPTY64) {
                 unsigned long long p = (w >> 1) & P_MASK;
                 atomicOr(&bm_node[p >> 5], 1u << (p & 31));
             }
         }
         if (s < ecap) {
-            unsigned long long key = etab[s].key;
-            if (key != EMPTY64) {
-                unsigned long long p = etab[s].ord >> 2;
+            unsigned long long key, eord;
+            unsigned int ecov;
+            if (ev.get(s, key, eord, ecov)) {
+                unsigned long long p = eord >> 2;
                 atomicOr(&bm_ea[p >> 5], 1u << (p & 31));
                 unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
                 if (lo != hi) atomicOr(&bm_eb[p >> 5], 1u << (p & 31));
@@ -450,19 +522,19 @@ __global__ void k_collect_sizes(const int64_t *__restrict__ win_off, int64_t R, 
     }
 }
 
-__global__ void k_emit_nodes(NodeSlot *__restrict__ ntab, unsigned int ncap, const int32_t *__restrict__ ids, int k,
+__global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids, int k,
                              const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
                              int32_t *__restrict__ node_key, uint32_t *__restrict__ node_cov,
                              int8_t *__restrict__ node_dir, int32_t *__restrict__ parent) {
     const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ncap; s += stride) {
-        unsigned long long w = ntab[s].word;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
+        unsigned long long w = nv.w(s);
         if (w == EMPTY64) continue;
         const unsigned long long p = (w >> 1) & P_MASK;
         const int neg = (int)(w & 1ull);
         const int idx = pref_node[p >> 5] + __popc(bm_node[p >> 5] & ((1u << (p & 31)) - 1u));
-        ntab[s].aux = (unsigned int)idx;
-        node_cov[idx] = ntab[s].cov + 1u;
+        nv.a(s) = (unsigned int)idx;
+        node_cov[idx] = nv.c(s) + 1u;
         node_dir[idx] = neg ? -1 : 1;
         parent[idx] = idx;
         for (int j = 0; j < k; ++j)
@@ -510,25 +582,25 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
     }
 }
 
-__global__ void k_emit_edges(const EdgeSlot *__restrict__ etab, unsigned int ecap, const NodeSlot *__restrict__ ntab,
+__global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
                              const unsigned int *__restrict__ bm_ea, const unsigned int *__restrict__ bm_eb,
                              const int *__restrict__ pref_edge, int32_t *__restrict__ e_src,
                              int32_t *__restrict__ e_tgt, int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td,
                              uint32_t *__restrict__ e_cov, int32_t *__restrict__ parent) {
     const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ecap; s += stride) {
-        const unsigned long long key = etab[s].key;
-        if (key == EMPTY64) continue;
-        const unsigned long long ord = etab[s].ord;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ev.cap; s += stride) {
+        unsigned long long key, ord;
+        unsigned int ecov;
+        if (!ev.get(s, key, ord, ecov)) continue;
         const unsigned long long p = ord >> 2;
         const unsigned int below = (1u << (p & 31)) - 1u;
         const int idx = pref_edge[p >> 5] + __popc(bm_ea[p >> 5] & below) + __popc(bm_eb[p >> 5] & below);
         const unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
         const int rel = (key & 1ull) ? 1 : -1;
         const bool src_hi = (ord >> 1) & 1ull;
-        const int src = (int)ntab[src_hi ? hi : lo].aux, tgt = (int)ntab[src_hi ? lo : hi].aux;
+        const int src = (int)nv.a(src_hi ? hi : lo), tgt = (int)nv.a(src_hi ? lo : hi);
         const int sd = (ord & 1ull) ? -1 : 1, td = rel * sd;
-        const uint32_t cov = etab[s].cov + 1u;
+        const uint32_t cov = ecov + 1u;
         if (lo != hi) {
             // forward edge S->T, then the reverse edge T->S with directions (-td, -sd)
             e_src[idx] = src; e_tgt[idx] = tgt; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = cov;
@@ -543,10 +615,10 @@ __global__ void k_emit_edges(const EdgeSlot *__restrict__ etab, unsigned int eca
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_remap_windows(const NodeSlot *__restrict__ ntab, int32_t *__restrict__ win_node, int64_t W) {
+__global__ void k_remap_windows(const NodeView nv, int32_t *__restrict__ win_node, int64_t W) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += stride)
-        win_node[w] = (int32_t)__ldg(&ntab[win_node[w]].aux);
+        win_node[w] = (int32_t)nv.a((unsigned int)win_node[w]);
 }
 
 // after the stable sort by node: duplicates (same node, same read) are adjacent.  Count them per
@@ -759,6 +831,31 @@ __global__ void k_atomic_cas(unsigned long long *__restrict__ table, unsigned lo
         acc += atomicCAS(&table[(unsigned long long)(((h >> 32) * n_slots) >> 32)], EMPTY64, h | 1ull);
     }
     if (acc == 0x123456789abcdefULL) table[0] = acc;  // keep the returns alive
+}
+
+// largest |id| of the input: decides how many bits a gene takes in the packed keys
+__global__ void k_max_abs(const int32_t *__restrict__ ids, int64_t G, unsigned int *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride) {
+        const int g = __ldg(ids + i);
+        m = max(m, (unsigned int)(g < 0 ? -(long long)g : (long long)g));
+    }
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// random 32-byte sector loads (LDG.E.256 at L2), the other half of a hash-table probe
+__global__ void k_random_load(const NodeSlot *__restrict__ table, unsigned long long n_slots, unsigned long long n_ops,
+                              unsigned long long seed, unsigned long long *__restrict__ sink) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_ops; i += stride) {
+        unsigned long long h = mix64(i + seed), a, b, c, d;
+        load_node_slot(&table[(unsigned long long)(((h >> 32) * n_slots) >> 32)], a, b, c, d);
+        acc += a ^ b ^ c ^ d;
+    }
+    if (acc == 0x123456789abcdefULL) *sink = acc;
 }
 
 }  // namespace amira

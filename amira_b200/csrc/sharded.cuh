@@ -39,7 +39,7 @@ __device__ __forceinline__ void load_canonical(const int32_t *ids, unsigned long
 
 // pass 1 / pass 2 over the local node table: count per owner, then scatter into the send buffer
 template <bool SCATTER>
-__global__ void k_node_route(NodeSlot *__restrict__ ntab, unsigned int ncap, const int32_t *__restrict__ ids, int k,
+__global__ void k_node_route(const NodeView nv, const int32_t *__restrict__ ids, int k,
                              int world, long long call_base, unsigned long long *__restrict__ counts,
                              const long long *__restrict__ dest_off, int32_t *__restrict__ s_key,
                              NodeRec *__restrict__ s_meta) {
@@ -50,8 +50,8 @@ __global__ void k_node_route(NodeSlot *__restrict__ ntab, unsigned int ncap, con
     }
     const unsigned int stride = gridDim.x * blockDim.x;
     int32_t key[MAX_K];
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ncap; s += stride) {
-        const unsigned long long w = ntab[s].word;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
+        const unsigned long long w = nv.w(s);
         if (w == EMPTY64) continue;
         load_canonical(ids, w, k, key);
         const int d = owner_of(canonical_hash(key, k, 0), world);
@@ -62,10 +62,10 @@ __global__ void k_node_route(NodeSlot *__restrict__ ntab, unsigned int ncap, con
             for (int j = 0; j < k; ++j) s_key[i * k + j] = key[j];
             NodeRec r;
             r.ord = ((unsigned long long)(call_base + (long long)((w >> 1) & P_MASK)) << 1) | (w & 1ull);
-            r.cov = ntab[s].cov + 1u;
+            r.cov = nv.c(s) + 1u;
             r.pad = 0;
             s_meta[i] = r;
-            ntab[s].aux = (unsigned int)i;
+            nv.a(s) = (unsigned int)i;
         }
     }
     if (!SCATTER) {
@@ -164,36 +164,35 @@ __device__ __forceinline__ long long node_lookup(const BuildParams &P, const int
 }
 
 // local node table: aux (index into the send buffer) -> global node index; local coverage per global node
-__global__ void k_local_to_global(NodeSlot *__restrict__ ntab, unsigned int ncap, const int32_t *__restrict__ s_key,
-                                  const BuildParams G, uint32_t *__restrict__ cov_local) {
+__global__ void k_local_to_global(const NodeView nv, const int32_t *__restrict__ s_key, const BuildParams G,
+                                  uint32_t *__restrict__ cov_local) {
     const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ncap; s += stride) {
-        if (ntab[s].word == EMPTY64) continue;
-        const long long i = ntab[s].aux;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
+        if (nv.w(s) == EMPTY64) continue;
+        const long long i = nv.a(s);
         const long long g = node_lookup(G, s_key + i * G.k);
-        ntab[s].aux = (unsigned int)g;
-        cov_local[g] = ntab[s].cov + 1u;
+        nv.a(s) = (unsigned int)g;
+        cov_local[g] = nv.c(s) + 1u;
     }
 }
 
 // ---- edges ----------------------------------------------------------------------------------------
-__device__ __forceinline__ EdgeSlot global_edge_record(const EdgeSlot &e, const NodeSlot *__restrict__ ntab,
-                                                      long long call_base) {
-    const unsigned int lo = (unsigned int)(e.key >> 32), hi = (unsigned int)((e.key & 0xFFFFFFFFull) >> 1);
-    const bool src_hi = (e.ord >> 1) & 1ull;
-    const unsigned int gs = ntab[src_hi ? hi : lo].aux, gt = ntab[src_hi ? lo : hi].aux;
+__device__ __forceinline__ EdgeSlot global_edge_record(unsigned long long key, unsigned long long ord, unsigned int cov,
+                                                      const NodeView &nv, long long call_base) {
+    const unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
+    const bool src_hi = (ord >> 1) & 1ull;
+    const unsigned int gs = nv.a(src_hi ? hi : lo), gt = nv.a(src_hi ? lo : hi);
     EdgeSlot r;
-    r.key = ((unsigned long long)min(gs, gt) << 32) | ((unsigned long long)max(gs, gt) << 1) | (e.key & 1ull);
-    r.ord = ((unsigned long long)(call_base + (long long)(e.ord >> 2)) << 2) | ((unsigned long long)(gs > gt) << 1) |
-            (e.ord & 1ull);
-    r.cov = e.cov + 1u;
+    r.key = ((unsigned long long)min(gs, gt) << 32) | ((unsigned long long)max(gs, gt) << 1) | (key & 1ull);
+    r.ord = ((unsigned long long)(call_base + (long long)(ord >> 2)) << 2) | ((unsigned long long)(gs > gt) << 1) |
+            (ord & 1ull);
+    r.cov = cov + 1u;
     r.pad[0] = r.pad[1] = r.pad[2] = 0;
     return r;
 }
 
 template <bool SCATTER>
-__global__ void k_edge_route(const EdgeSlot *__restrict__ etab, unsigned int ecap, const NodeSlot *__restrict__ ntab,
-                             int world, long long call_base, unsigned long long *__restrict__ counts,
+__global__ void k_edge_route(const EdgeView ev, const NodeView nv, int world, long long call_base, unsigned long long *__restrict__ counts,
                              const long long *__restrict__ dest_off, EdgeSlot *__restrict__ s_edges) {
     __shared__ unsigned int s_cnt[MAX_WORLD];
     if (!SCATTER) {
@@ -201,10 +200,11 @@ __global__ void k_edge_route(const EdgeSlot *__restrict__ etab, unsigned int eca
         __syncthreads();
     }
     const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ecap; s += stride) {
-        EdgeSlot e = etab[s];
-        if (e.key == EMPTY64) continue;
-        const EdgeSlot r = global_edge_record(e, ntab, call_base);
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ev.cap; s += stride) {
+        unsigned long long ekey, eord;
+        unsigned int ecov;
+        if (!ev.get(s, ekey, eord, ecov)) continue;
+        const EdgeSlot r = global_edge_record(ekey, eord, ecov, nv, call_base);
         const int d = owner_of(mix64(r.key), world);
         if (!SCATTER) atomicAdd(&s_cnt[d], 1u);
         else s_edges[dest_off[d] + (long long)atomicAdd(&counts[d], 1ull)] = r;

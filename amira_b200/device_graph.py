@@ -101,10 +101,15 @@ class DeviceGraph:
         _lib.check(self._lib.amira_gmg_kernel_launches(self._h, C.byref(n)))
         return n.value
 
+    def debug_layout(self, mask: int):
+        """test hook: 1 = no 16-byte node slots, 2 = no 16-byte edge slots, 4 = no packed keys"""
+        _lib.check(self._lib.amira_gmg_debug_layout(self._h, int(mask)))
+
     def atomic_peak(self, table_bytes: int, n_ops: int):
-        a, b = C.c_double(), C.c_double()
-        _lib.check(self._lib.amira_gmg_atomic_peak(self._h, int(table_bytes), int(n_ops), C.byref(a), C.byref(b)))
-        return a.value, b.value
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(self._lib.amira_gmg_atomic_peak(self._h, int(table_bytes), int(n_ops), C.byref(a), C.byref(b),
+                                                   C.byref(c)))
+        return a.value, b.value, c.value
 
     # ---- multi-GPU: one process per GPU, contiguous read shards in rank order ----------------------
     def nccl_unique_id(self) -> np.ndarray:

@@ -236,6 +236,11 @@ def run_gpu(args):
     def step_device():
         dg.build(d_ids, d_off, k, on_device=True)
 
+    if args.table_load > 0:              # developer experiment: hash-table load factor
+        step_device()
+        s0 = dg.sizes()
+        dg.reserve(int(s0["nodes"] / (2 * args.table_load)), int(s0["edges"] / 2 / (2 * args.table_load)))
+
     for _ in range(args.warmup):
         step_device()
     dg.sync()
@@ -341,9 +346,10 @@ def run_gpu(args):
                 "whole_build_frac": round(bytes_alg / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak, 4)}
     if rank == 0 and not args.no_atomic_peak:
         # the second roofline of SURVEY.md 8(d): algorithmic atomics / measured random-address atomic rate
-        red, cas = dg.atomic_peak(64 << 20, 1 << 26)
+        red, cas, ld = dg.atomic_peak(64 << 20, 1 << 26)
         t_atomic_ms = ATOMICS_PER_GENE_MER * W / red * 1e3
-        roofline["atomic"] = {"red_add_per_s": red, "cas_per_s": cas, "table": "64 MB (L2 resident)",
+        roofline["atomic"] = {"red_add_per_s": red, "cas_per_s": cas, "sector_load_per_s": ld,
+                              "table": "64 MB (L2 resident)",
                               "atomics_per_gene_mer": ATOMICS_PER_GENE_MER,
                               "kernel_frac": round(t_atomic_ms / kernel_ms, 4),
                               "whole_build_frac": round(t_atomic_ms / (ms_total / args.steps), 4)}
@@ -411,6 +417,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-atomic-peak", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--table-load", type=float, default=0.0, help="experiment: hash tables sized to this load factor")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -59,9 +59,11 @@ enum {
     AMIRA_PH_COMPONENTS = 7, /* connected components */
     AMIRA_PH_FILTER = 8,     /* last filter / component removal */
     AMIRA_PH_EXCHANGE = 9,   /* multi-GPU all-to-all + merge */
-    AMIRA_PH_EMIT = 10,      /* node / edge arrays in first-seen order + union-find */
+    AMIRA_PH_EMIT = 10,      /* edge arrays in first-seen order + union-find (second stream, beside REMAP / INCIDENCE,
+                              * as are ADJACENCY and COMPONENTS) */
     AMIRA_PH_INSERT_KERNEL = 11, /* k_insert_windows alone (inside AMIRA_PH_INSERT, which also clears the tables) */
-    AMIRA_PH_COUNT = 12
+    AMIRA_PH_EMIT_NODES = 12,    /* node arrays in first-seen order */
+    AMIRA_PH_COUNT = 13
 };
 
 const char *amira_last_error(void);
@@ -144,10 +146,16 @@ int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edg
 int amira_gmg_nccl_unique_id(void *out_128_bytes);
 int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int world);
 
-/* Micro-benchmark for the atomic roofline: random-address 32-bit RED.ADD and 64-bit
- * CAS into a table of table_bytes; returns operations per second of each. */
+/* Test hook: forbid table layouts the library would otherwise choose from the input, so that the
+ * rarely taken ones are exercised at small sizes.  mask bits: 1 = no 16-byte node slots, 2 = no
+ * 16-byte edge slots, 4 = no packed keys (gene-mers compared through the ids array). */
+int amira_gmg_debug_layout(amira_gmg *h, int mask);
+
+/* Micro-benchmark for the atomic roofline: random-address 32-bit RED.ADD, 64-bit CAS
+ * and (if load_per_s is non-NULL) 32-byte sector loads into a table of table_bytes; returns
+ * operations per second of each. */
 int amira_gmg_atomic_peak(amira_gmg *h, int64_t table_bytes, int64_t n_ops, double *red_add_per_s,
-                          double *cas_per_s);
+                          double *cas_per_s, double *load_per_s);
 
 #ifdef __cplusplus
 }

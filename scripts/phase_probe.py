@@ -34,8 +34,8 @@ def run(name, n_reads, k=None, reps=5):
 
 if __name__ == "__main__":
     g = DeviceGraph(0)
-    for mb in (1, 16, 64, 512):
-        print("atomic peak table %d MB: red/s %.3g cas/s %.3g" % ((mb,) + g.atomic_peak(mb << 20, 1 << 26)))
+    for mb in (1, 16, 64, 128, 192, 512):
+        print("random-access peak, table %d MB: red/s %.3g cas/s %.3g 32B-load/s %.3g" % ((mb,) + g.atomic_peak(mb << 20, 1 << 26)))
     g.close()
     run("c2", 50000)
     run("c3", 500000)

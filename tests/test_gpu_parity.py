@@ -67,6 +67,42 @@ def test_gpu_matches_c_oracle_on_synthetic(dg, cfg_name, n_reads, k, with_pos):
     assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
 
 
+@pytest.mark.parametrize("mask", [1, 2, 3, 5, 7])
+@pytest.mark.parametrize("cfg_name,n_reads,k", [("c3", 30000, 3), ("c5", 20000, 5), ("c4", 20000, 7)])
+def test_gpu_every_table_layout(dg, mask, cfg_name, n_reads, k):
+    """32-byte node slots (packed and unpacked keys) and 32-byte edge slots give the same graph as the 16-byte ones"""
+    from amira_b200 import synth
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    ids, off = synth.generate(synth.CONFIGS[cfg_name], 0, n_reads)
+    ref = c_oracle.COracleGraph(ids, off, k)
+    dg.debug_layout(mask)
+    try:
+        dg.build(ids, off, k)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
+        ref.remove_low_coverage_components(5)
+        dg.remove_low_coverage_components(5)
+        ref.filter_graph(3, 1)
+        dg.filter_graph(3, 1)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
+    finally:
+        dg.debug_layout(0)
+
+
+def test_gpu_id_width_is_remeasured(dg):
+    """a handle that has only seen small gene ids must notice larger ones (packed keys are sized from the largest |id|)"""
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    rng = np.random.default_rng(5)
+    off = np.arange(0, 3001, 30).astype(np.int64)
+    for vmax in (20, 5000, 2_000_000, 900_000_000, 50):
+        ids = (rng.integers(1, vmax + 1, off[-1]) * rng.choice([-1, 1], off[-1])).astype(np.int32)
+        ids[:40] = np.tile(ids[:5], 8)           # some repeats so that nodes get coverage > 1
+        for k in (3, 5):
+            dg.build(ids, off, k)
+            assert O.diff_arrays(dg.arrays(), c_oracle.COracleGraph(ids, off, k).arrays()) == [], (vmax, k)
+
+
 def test_gpu_edge_cases(dg):
     from oracle import c_oracle
     from oracle import gmg_oracle as O
