@@ -286,6 +286,8 @@ int do_build(amira_gmg *h) {
         h->e16 = e16;
         ncap = std::min<int64_t>(ncap, 0x7FFFFFF0ll);
         ecap = std::min<int64_t>(ecap, 0x7FFFFFF0ll);
+        ncap &= ~1ll;  // buckets of two slots
+        ecap &= ~1ll;
         h->ncap = (unsigned int)ncap;
         h->ecap = (unsigned int)ecap;
         const size_t nbytes = n16 ? (sizeof(NodeSlot16) + 2 * sizeof(unsigned int)) * (size_t)ncap : sizeof(NodeSlot) * (size_t)ncap;
@@ -319,6 +321,7 @@ int do_build(amira_gmg *h) {
                 P.status = h->d_status.as<int>();
                 P.read_base = h->first_read_global;
                 P.key_bits = key_bits;
+                P.count_cov = h->world > 1;
                 P.ids_aligned = (reinterpret_cast<uintptr_t>(h->ids) & 15) == 0;
                 const int grid = (int)std::min<int64_t>((n_tiles + INS_WARPS - 1) / INS_WARPS,
                                                         (int64_t)h->n_sm * h->insert_ctas_per_sm);
@@ -337,6 +340,10 @@ int do_build(amira_gmg *h) {
                 else INSERT_K(0);
 #undef INSERT_K
 #undef INSERT_KE
+                if (n_tiles > 1) {
+                    if (e16) LAUNCH(h, k_boundary_edges<true>, grid_for(n_tiles - 1, 256), 256, P);
+                    else LAUNCH(h, k_boundary_edges<false>, grid_for(n_tiles - 1, 256), 256, P);
+                }
             }
         }
         if (h->world > 1) {
@@ -410,7 +417,7 @@ int do_build(amira_gmg *h) {
         AMIRA_TRY(h->is_root.reserve(sizeof(int) * (N + 2)));
         if (N > 0) {
             LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->nview, h->ids, k, bm_node,
-                   h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
+                   h->cnt_node.as<int>(), h->node_key.as<int32_t>(), (uint32_t *)nullptr /* from the sort */,
                    h->node_dir.as<int8_t>(), h->parent.as<int32_t>());
         }
     }
@@ -423,7 +430,7 @@ int do_build(amira_gmg *h) {
     AMIRA_TRY(h->cc_min.reserve(sizeof(unsigned int) * (N + 1)));
     AMIRA_TRY(h->reads_off.reserve(sizeof(int64_t) * (N + 2)));
     AMIRA_TRY(h->reads.reserve(sizeof(int32_t) * std::max<int64_t>(1, W)));
-    AMIRA_TRY(h->dups.reserve(sizeof(uint32_t) * (N + 1)));
+    AMIRA_TRY(h->dups.reserve(sizeof(uint32_t) * 2 * (N + 1)));  // duplicates per node, then run starts
     if (W > 0) {
         AMIRA_TRY(h->sort_keys.reserve(sizeof(int32_t) * W));
         AMIRA_TRY(h->sort_vals.reserve(sizeof(int32_t) * W));
@@ -471,7 +478,8 @@ int do_build(amira_gmg *h) {
                                                        h->win_read.as<int32_t>(), h->sort_vals.as<int32_t>(), W, 0, bits, st);
             }));
             LAUNCH(h, k_incidence_flags, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->sort_keys.as<int32_t>(),
-                   h->sort_vals.as<int32_t>(), W, h->flags.as<uint8_t>(), h->dups.as<uint32_t>());
+                   h->sort_vals.as<int32_t>(), W, h->flags.as<uint8_t>(), h->dups.as<uint32_t>(),
+                   h->dups.as<uint32_t>() + (N + 1));
             AMIRA_TRY(cub_call(h, [&](void *t, size_t &b) {
                 return cub::DeviceSelect::Flagged(t, b, h->sort_vals.as<int32_t>(), h->flags.as<uint8_t>(),
                                                   h->reads.as<int32_t>(), h->d_nsel.as<long long>(), W, st);
@@ -480,9 +488,10 @@ int do_build(amira_gmg *h) {
         if (W > 0 && h->first_read_global != 0)  // Node.listOfReads holds global read indices
             LAUNCH(h, k_add_i32, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->reads.as<int32_t>(), (long long)W,
                    (int32_t)h->first_read_global);
+        // one GPU: every node has at least one window, so every run start was written
         LAUNCH(h, k_incidence_counts, grid_for(N + 1, 256), 256,
-               h->world > 1 ? h->cov_local.as<uint32_t>() : h->node_cov.as<uint32_t>(), h->dups.as<uint32_t>(), N,
-               h->reads_off.as<int64_t>());
+               h->world > 1 ? h->cov_local.as<uint32_t>() : h->node_cov.as<uint32_t>(), h->dups.as<uint32_t>() + (N + 1),
+               h->dups.as<uint32_t>(), N, W, h->world > 1 ? 0 : 1, h->reads_off.as<int64_t>());
         AMIRA_TRY(exclusive_sum_inplace(h, h->reads_off.as<int64_t>(), N + 1));
     }
     AMIRA_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));

@@ -66,6 +66,8 @@ struct BuildParams {
     int32_t *win_end;
     int *status;
     int64_t read_base;  // global index of this shard's first read (multi-GPU)
+    int count_cov;      // bump the slot's coverage per window (multi-GPU: the merge needs local counts before the
+                        // sort; on one GPU coverage is the run length of the node in the incidence sort instead)
     int key_bits;       // bits per gene of the packed key (<= 124 bits); 0: gene-mers are compared through ids
     int ids_aligned;    // ids is 16-byte aligned (128-bit staging loads)
 };
@@ -218,60 +220,80 @@ __device__ __forceinline__ void load_slot16(const void *s, unsigned long long &a
     asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(s));
 }
 
+__device__ __forceinline__ void load_bucket(const void *s, unsigned long long &a0, unsigned long long &b0,
+                                            unsigned long long &a1, unsigned long long &b1) {
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a0), "=l"(b0), "=l"(a1), "=l"(b1) : "l"(s));
+}
+
+// The 16-byte tables are probed by BUCKETS of two slots = one 32-byte sector: one LDG.256 brings
+// both, a gene-mer lives in the first free slot of the first bucket with room (slots never empty
+// again, so a search stops at the first empty slot).  At 50% load that is ~1.1 sector loads per
+// lookup with a short tail, against ~1.5 and a long tail for slot-wise linear probing -- and the
+// tail is what a warp pays for, since its lanes wait for the longest probe sequence among them.
+//
 // mine = (top 22 key bits) << 42 | first position << 1 | first direction; keylow = low 63 key bits
 __device__ __forceinline__ unsigned int node_insert16(const BuildParams &P, const int32_t *win, int dirneg,
                                                       unsigned long long keylow, unsigned long long h,
                                                       unsigned long long mine) {
-    const unsigned int cap = P.ncap;
-    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
+    const unsigned int nb = P.ncap >> 1;
+    unsigned int b = (unsigned int)(((unsigned long long)(unsigned int)h * nb) >> 32);
     const unsigned int top = (unsigned int)(mine >> FP_SHIFT);
     for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
-        unsigned long long cur, key;
-        load_slot16(&P.ntab16[s], cur, key);
-        if (cur == EMPTY64) {
-            unsigned long long old = atomicCAS(&P.ntab16[s].word, EMPTY64, mine);
-            if (old == EMPTY64) {
-                __stcg(&P.ntab16[s].key, keylow);
-                return s;
+        NodeSlot16 *B = P.ntab16 + 2 * (size_t)b;
+        unsigned long long w0, k0, w1, k1;
+        load_bucket(B, w0, k0, w1, k1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            unsigned long long cur = i ? w1 : w0, key = i ? k1 : k0;
+            if (cur == EMPTY64) {
+                unsigned long long old = atomicCAS(&B[i].word, EMPTY64, mine);
+                if (old == EMPTY64) {
+                    __stcg(&B[i].key, keylow);
+                    return 2 * b + i;
+                }
+                cur = old;
+                key = EMPTY64;
             }
-            cur = old;
-            key = EMPTY64;
-        }
-        if ((unsigned int)(cur >> FP_SHIFT) == top) {
-            const bool same = (key != EMPTY64) ? (key == keylow) : same_as_representative(P, win, dirneg, cur);
-            if (same) {
-                if (mine < cur) atomicMin(&P.ntab16[s].word, mine);  // keep the first occurrence
-                return s;
+            if ((unsigned int)(cur >> FP_SHIFT) == top) {
+                const bool same = (key != EMPTY64) ? (key == keylow) : same_as_representative(P, win, dirneg, cur);
+                if (same) {
+                    if (mine < cur) atomicMin(&B[i].word, mine);  // keep the first occurrence
+                    return 2 * b + i;
+                }
             }
         }
-        if (++s == cap) s = 0;
+        if (++b == nb) b = 0;
     }
     P.status[ST_OVERFLOW_N] = 1;
     return 0;
 }
 
 __device__ __forceinline__ void edge_insert16(const BuildParams &P, unsigned long long key, unsigned int ord) {
-    const unsigned int cap = P.ecap;
+    const unsigned int nb = P.ecap >> 1;
     unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
     h ^= h >> 32;
     h *= 0xD6E8FEB86659FD93ULL;
-    unsigned int s = (unsigned int)(h >> 32);
-    s = (unsigned int)(((unsigned long long)s * cap) >> 32);
+    unsigned int b = (unsigned int)(((h >> 32) * nb) >> 32);
     for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
-        unsigned long long cur, co;
-        load_slot16(&P.etab16[s], cur, co);
-        unsigned int cord = (unsigned int)(co >> 32);
-        if (cur == EMPTY64) {
-            unsigned long long old = atomicCAS(&P.etab16[s].key, EMPTY64, key);
-            cur = (old == EMPTY64) ? key : old;
-            cord = 0xFFFFFFFFu;
+        EdgeSlot16 *B = P.etab16 + 2 * (size_t)b;
+        unsigned long long c0, o0, c1, o1;
+        load_bucket(B, c0, o0, c1, o1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            unsigned long long cur = i ? c1 : c0;
+            unsigned int cord = (unsigned int)((i ? o1 : o0) >> 32);
+            if (cur == EMPTY64) {
+                unsigned long long old = atomicCAS(&B[i].key, EMPTY64, key);
+                cur = (old == EMPTY64) ? key : old;
+                cord = 0xFFFFFFFFu;
+            }
+            if (cur == key) {
+                if (ord < cord) atomicMin(&B[i].ord, ord);
+                atomicAdd(&B[i].cov, 1u);
+                return;
+            }
         }
-        if (cur == key) {
-            if (ord < cord) atomicMin(&P.etab16[s].ord, ord);
-            atomicAdd(&P.etab16[s].cov, 1u);
-            return;
-        }
-        if (++s == cap) s = 0;
+        if (++b == nb) b = 0;
     }
     P.status[ST_OVERFLOW_E] = 1;
 }
@@ -365,11 +387,11 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
         }
         __syncwarp();
 
-        // ---- windows: pl == len is the halo window that only serves the last pair of the chunk
+        // ---- windows (the pair that straddles two chunks is left to k_boundary_edges)
 #pragma unroll 1
-        for (int pl = lane; pl <= len; pl += 32) {
-            const bool halo = (pl == len);
-            const int j = S.j[halo ? pl - 1 : pl];
+        for (int pl = lane; pl < len; pl += 32) {
+            const bool halo = false;
+            const int j = S.j[pl];
             const int64_t p = c0 + pl;
             const long long re = (j <= NR_STAGE) ? S.off[j + 1] : P.off[r_lo + j + 1];
             unsigned int val = INVALID_VAL;
@@ -433,7 +455,7 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
                     }
                     val = slot | ((unsigned int)dirneg << 31);
                     if (!halo) {
-                        atomicAdd(N16 ? &P.ncov[slot] : &P.ntab[slot].cov, 1u);
+                        if (P.count_cov) atomicAdd(N16 ? &P.ncov[slot] : &P.ntab[slot].cov, 1u);
                         const long long rs = (j <= NR_STAGE + 1) ? S.off[j] : P.off[r_lo + j];
                         const long long wo = (j <= NR_STAGE) ? S.woff[j] : P.win_off[r_lo + j];
                         const int64_t w = wo + (p - rs);
@@ -452,10 +474,10 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
         __syncwarp();
         // ---- adjacent pairs of the same read
 #pragma unroll 1
-        for (int pl = lane; pl < len; pl += 32) {
+        for (int pl = lane; pl + 1 < len; pl += 32) {
             const unsigned int a = S.val[pl], b = S.val[pl + 1];
             if (a == INVALID_VAL || b == INVALID_VAL) continue;
-            if (pl + 1 < len && S.j[pl + 1] != S.j[pl]) continue;
+            if (S.j[pl + 1] != S.j[pl]) continue;
             const unsigned int sa = a & 0x7FFFFFFFu, sb = b & 0x7FFFFFFFu;
             const unsigned int sdneg = a >> 31, tdneg = b >> 31;
             const unsigned int lo = min(sa, sb), hi = max(sa, sb);
@@ -468,6 +490,27 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
         }
         __syncwarp();
     }
+}
+
+// The adjacent pair whose two windows start in different chunks (last call of chunk c-1, first call
+// of chunk c): both windows were inserted by their own chunks, their slots are in win_node.
+template <bool E16>
+__global__ void k_boundary_edges(const BuildParams P) {
+    const int64_t c = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_tiles) return;
+    const int64_t p1 = c * WC, p0 = p1 - 1;
+    const int r = P.tile_r0[c];
+    const int64_t rs = P.off[r], re = P.off[r + 1];
+    if (rs > p0 || p1 + P.k > re) return;  // different reads, or no window starts at p1
+    const int64_t w0 = P.win_off[r] + (p0 - rs);
+    const unsigned int sa = (unsigned int)P.win_node[w0], sb = (unsigned int)P.win_node[w0 + 1];
+    const unsigned int sdneg = P.win_dir[w0] < 0, tdneg = P.win_dir[w0 + 1] < 0;
+    const unsigned int lo = min(sa, sb), hi = max(sa, sb);
+    const unsigned long long key =
+        ((unsigned long long)lo << 32) | ((unsigned long long)hi << 1) | (unsigned long long)(sdneg == tdneg);
+    const unsigned long long ord = ((unsigned long long)p0 << 2) | ((unsigned long long)(sa > sb) << 1) | sdneg;
+    if (E16) edge_insert16(P, key, (unsigned int)ord);
+    else edge_insert(P, key, ord);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -534,7 +577,7 @@ __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids,
         const int neg = (int)(w & 1ull);
         const int idx = pref_node[p >> 5] + __popc(bm_node[p >> 5] & ((1u << (p & 31)) - 1u));
         nv.a(s) = (unsigned int)idx;
-        node_cov[idx] = nv.c(s) + 1u;
+        if (node_cov) node_cov[idx] = nv.c(s) + 1u;
         node_dir[idx] = neg ? -1 : 1;
         parent[idx] = idx;
         for (int j = 0; j < k; ++j)
@@ -622,22 +665,39 @@ __global__ void k_remap_windows(const NodeView nv, int32_t *__restrict__ win_nod
 }
 
 // after the stable sort by node: duplicates (same node, same read) are adjacent.  Count them per
-// node (rare) and flag the survivors.
+// node (rare), flag the survivors, and record where each node's run starts: the run length is the
+// node's coverage (construct_graph.py:71,86,100 counts one per window).
 __global__ void k_incidence_flags(const int32_t *__restrict__ keys, const int32_t *__restrict__ vals, int64_t W,
-                                  uint8_t *__restrict__ flags, uint32_t *__restrict__ dups) {
+                                  uint8_t *__restrict__ flags, uint32_t *__restrict__ dups,
+                                  uint32_t *__restrict__ run_start) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < W; i += stride) {
-        bool first = (i == 0) || keys[i] != keys[i - 1] || vals[i] != vals[i - 1];
+        const int32_t key = keys[i];
+        const bool new_node = (i == 0) || key != keys[i - 1];
+        const bool first = new_node || vals[i] != vals[i - 1];
         flags[i] = first;
-        if (!first) atomicAdd(&dups[keys[i]], 1u);
+        if (!first) atomicAdd(&dups[key], 1u);
+        if (new_node) run_start[key] = (uint32_t)i;
     }
 }
 
-__global__ void k_incidence_counts(const uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ dups,
-                                   int64_t n_nodes, int64_t *__restrict__ reads_off) {
+// per-node number of unique reads; cov_from_runs: also the coverage, from the run lengths
+__global__ void k_incidence_counts(uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ run_start,
+                                   const uint32_t *__restrict__ dups, int64_t n_nodes, int64_t W, int cov_from_runs,
+                                   int64_t *__restrict__ reads_off) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) reads_off[i] = (int64_t)node_cov[i] - (int64_t)dups[i];
-    else if (i == n_nodes) reads_off[i] = 0;
+    if (i < n_nodes) {
+        uint32_t cov;
+        if (cov_from_runs) {
+            cov = (i + 1 < n_nodes ? run_start[i + 1] : (uint32_t)W) - run_start[i];
+            node_cov[i] = cov;
+        } else {
+            cov = node_cov[i];
+        }
+        reads_off[i] = (int64_t)cov - (int64_t)dups[i];
+    } else if (i == n_nodes) {
+        reads_off[i] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
