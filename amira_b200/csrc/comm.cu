@@ -79,6 +79,14 @@ int load_nccl() {
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory window: one cudaMalloc'ed buffer per rank, mapped into every other rank of the node
+    // through CUDA IPC, so that the routing kernels store records straight into the owner's memory
+    // over NVLink instead of staging them for ncclSend / ncclRecv
+    bool p2p_ok = true;          // until a mapping attempt fails on some rank
+    void *win_local = nullptr;
+    size_t win_bytes = 0;
+    void *win_peer[64] = {};
+    void *d_scratch = nullptr;   // 128 B per rank: IPC handles / flags travel through NCCL
 };
 
 int comm_unique_id(void *out_128_bytes) {
@@ -108,12 +116,114 @@ int comm_create(Comm **out, const void *unique_id, int rank, int world) {
         delete c;
         return AMIRA_E_NCCL;
     }
+    if (cudaMalloc(&c->d_scratch, 128 * (size_t)(world + 1)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of the communicator scratch failed");
+        g_nccl.CommDestroy(c->comm);
+        delete c;
+        return AMIRA_E_NOMEM;
+    }
+    cudaMemset(c->d_scratch, 0, 128 * (size_t)(world + 1));
     *out = c;
+    return AMIRA_OK;
+}
+
+int comm_barrier(Comm *c, cudaStream_t st);
+
+static void window_unmap_peers(Comm *c) {
+    for (int p = 0; p < c->world; ++p) {
+        if (p != c->rank && c->win_peer[p]) cudaIpcCloseMemHandle(c->win_peer[p]);
+        c->win_peer[p] = nullptr;
+    }
+}
+
+static void window_close(Comm *c) {
+    window_unmap_peers(c);
+    if (c->win_local) cudaFree(c->win_local);
+    c->win_local = nullptr;
+    c->win_bytes = 0;
+}
+
+// Collective.  Makes every rank's window at least `need_bytes` large (the same value on all ranks)
+// and maps all windows into this process.  Returns AMIRA_OK with comm_p2p(c) == false if peer
+// mapping is not possible on this node (the caller then uses the NCCL send/recv path).
+int comm_window_ensure(Comm *c, size_t need_bytes, cudaStream_t st) {
+    if (!c->p2p_ok) return AMIRA_OK;
+    if (need_bytes <= c->win_bytes) return AMIRA_OK;
+    AMIRA_CUDA(cudaStreamSynchronize(st));
+    if (c->win_local) {
+        // an exported allocation may only be freed once every importer has unmapped it
+        window_unmap_peers(c);
+        AMIRA_TRY(comm_barrier(c, st));
+        AMIRA_CUDA(cudaStreamSynchronize(st));
+        window_close(c);
+    }
+    const size_t bytes = need_bytes + need_bytes / 4 + (1 << 20);
+    int ok = 1;
+    if (cudaMalloc(&c->win_local, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        c->win_local = nullptr;
+        ok = 0;
+    }
+    struct Msg {
+        cudaIpcMemHandle_t handle;
+        int ok;
+        int pad[15];
+    } mine, all[64];
+    static_assert(sizeof(Msg) == 128, "message is 128 bytes");
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine.handle, c->win_local) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    mine.ok = ok;
+    char *d = (char *)c->d_scratch;
+    AMIRA_CUDA(cudaMemcpyAsync(d, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    AMIRA_NCCL(g_nccl.AllGather(d, d + 128, sizeof(Msg), ncclInt8, c->comm, st));
+    AMIRA_CUDA(cudaMemcpyAsync(all, d + 128, sizeof(Msg) * c->world, cudaMemcpyDeviceToHost, st));
+    AMIRA_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < c->world; ++p) ok &= all[p].ok;
+    if (ok) {
+        for (int p = 0; p < c->world && ok; ++p) {
+            if (p == c->rank) {
+                c->win_peer[p] = c->win_local;
+            } else if (cudaIpcOpenMemHandle(&c->win_peer[p], all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                c->win_peer[p] = nullptr;
+                ok = 0;
+            }
+        }
+    }
+    // every rank must take the same path: agree on the outcome
+    int *flag = (int *)c->d_scratch;
+    AMIRA_CUDA(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    AMIRA_NCCL(g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMin, c->comm, st));
+    AMIRA_CUDA(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AMIRA_CUDA(cudaStreamSynchronize(st));
+    if (!ok) {
+        window_close(c);
+        c->p2p_ok = false;
+        return AMIRA_OK;
+    }
+    c->win_bytes = bytes;
+    return AMIRA_OK;
+}
+
+bool comm_p2p(const Comm *c) { return c && c->p2p_ok && c->world > 1 && !getenv("AMIRA_NO_P2P"); }
+void *comm_window(const Comm *c, int p) { return c->win_peer[p]; }
+
+// all ranks' earlier work on `st` (including stores into peer windows) is complete and visible
+// when the barrier completes on `st`
+int comm_barrier(Comm *c, cudaStream_t st) {
+    int *flag = (int *)c->d_scratch + 16;
+    AMIRA_NCCL(g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMax, c->comm, st));
     return AMIRA_OK;
 }
 
 void comm_destroy(Comm *c) {
     if (!c) return;
+    window_close(c);
+    if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
 }

@@ -174,6 +174,10 @@ int comm_alltoallv(Comm *c, const void *d_send, const int64_t *send_off, void *d
                    size_t elem_bytes, cudaStream_t st);
 int comm_allgatherv(Comm *c, const void *d_send, int64_t n_send, void *d_recv, const int64_t *recv_off,
                     size_t elem_bytes, cudaStream_t st);
+int comm_window_ensure(Comm *c, size_t need_bytes, cudaStream_t st);  // collective; same need_bytes on every rank
+bool comm_p2p(const Comm *c);
+void *comm_window(const Comm *c, int p);
+int comm_barrier(Comm *c, cudaStream_t st);
 
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33;

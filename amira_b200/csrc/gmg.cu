@@ -90,7 +90,9 @@ struct amira_gmg {
     // multi-GPU (sharded.cuh): exchange scratch, local coverage per global node
     Comm *comm = nullptr;
     int rank = 0, world = 1;
-    int64_t first_read_global = 0, first_call_global = 0;
+    int64_t first_read_global = 0, first_call_global = 0, calls_global = 0;
+    int64_t sh_Eg = 0;               // merged undirected edge records of the current sharded build
+    const EdgeSlot *sh_gedge = nullptr;
     DevBuf x_cnt, x_skey, x_smeta, x_rkey, x_rmeta, x_rkey2, x_rmeta2, x_mkey, x_mmeta, x_gkey, x_gmeta, x_tab,
         x_sortk, x_sortk2, x_sorti, x_sorti2, x_sedge, x_redge, x_medge, x_gedge, x_etab, x_fan, cov_local;
     long long *h_cnt = nullptr;  // pinned, world*world + 4
@@ -148,6 +150,12 @@ struct SideStream {
         h->cur_temp = &h->cub_temp;
     }
 };
+
+int bits_for64(int64_t n) {
+    int b = 1;
+    while (b < 62 && (1ll << b) < n) ++b;
+    return b;
+}
 
 int bits_for(int64_t n) {
     int b = 1;
@@ -447,6 +455,12 @@ int do_build(amira_gmg *h) {
                    h->cnt_edge.as<int>(), h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
                    h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->parent.as<int32_t>());
         }
+        if (h->world > 1 && h->sh_Eg > 0) {
+            Phase ph(h, AMIRA_PH_EMIT);
+            LAUNCH(h, k_emit_edges_sorted, grid_for(h->sh_Eg, 256), 256, h->x_sorti2.as<unsigned int>(), h->sh_gedge,
+                   h->x_fan.as<int>(), (long long)h->sh_Eg, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(),
+                   h->e_sd.as<int8_t>(), h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->parent.as<int32_t>());
+        }
         AMIRA_TRY(build_adjacency(h));
         {
             Phase ph(h, AMIRA_PH_COMPONENTS);
@@ -599,16 +613,18 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
 // ---- multi-GPU: merge the local tables of all ranks into the global node / edge arrays ----------
 // (see sharded.cuh for the scheme)
 int sort_by_ord(amira_gmg *h, long long n) {
-    // x_sortk / x_sorti -> x_sortk2 / x_sorti2; positions use P_BITS bits plus two flag bits
+    // x_sortk / x_sorti -> x_sortk2 / x_sorti2; keys are a global call position plus two flag bits
     if (n <= 0) return AMIRA_OK;
+    const int bits = std::min(P_BITS + 3, bits_for64(h->calls_global + 1) + 2);
     return cub_call(h, [&](void *t, size_t &b) {
         return cub::DeviceRadixSort::SortPairs(t, b, h->x_sortk.as<unsigned long long>(),
                                                h->x_sortk2.as<unsigned long long>(), h->x_sorti.as<unsigned int>(),
-                                               h->x_sorti2.as<unsigned int>(), n, 0, P_BITS + 3, h->stream);
+                                               h->x_sorti2.as<unsigned int>(), n, 0, bits, h->cur);
     });
 }
 
-// counts[world] on the device -> the world x world matrix on the host; fills send_off / recv_off
+// counts[world] on the device -> the world x world matrix on the host (h_cnt[src * world + dst]);
+// fills send_off / recv_off of this rank and zeroes the cursors for the scatter pass
 int exchange_counts(amira_gmg *h, std::vector<int64_t> &send_off, std::vector<int64_t> &recv_off) {
     const int world = h->world, me = h->rank;
     unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
@@ -616,6 +632,7 @@ int exchange_counts(amira_gmg *h, std::vector<int64_t> &send_off, std::vector<in
     AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_mat, sizeof(unsigned long long) * world, h->stream));
     AMIRA_CUDA(cudaMemcpyAsync(h->h_cnt, d_mat, sizeof(unsigned long long) * world * world, cudaMemcpyDeviceToHost,
                                h->stream));
+    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, h->stream));
     AMIRA_CUDA(cudaStreamSynchronize(h->stream));
     send_off.assign(world + 1, 0);
     recv_off.assign(world + 1, 0);
@@ -623,13 +640,19 @@ int exchange_counts(amira_gmg *h, std::vector<int64_t> &send_off, std::vector<in
         send_off[p + 1] = send_off[p] + h->h_cnt[(int64_t)me * world + p];
         recv_off[p + 1] = recv_off[p] + h->h_cnt[(int64_t)p * world + me];
     }
-    // destination offsets for the scatter pass, cursors back to zero
-    long long *d_off = (long long *)(d_cnt + MAX_WORLD);
-    AMIRA_CUDA(cudaMemcpyAsync(d_off, send_off.data(), sizeof(long long) * world, cudaMemcpyHostToDevice, h->stream));
-    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, h->stream));
-    AMIRA_CUDA(cudaStreamSynchronize(h->stream));  // send_off lives on this stack frame's caller
     return AMIRA_OK;
 }
+
+// from the count matrix: records owner d receives in total, and where this rank's block starts there
+void owner_layout(const amira_gmg *h, int d, int64_t &n_recv, int64_t &my_start) {
+    n_recv = my_start = 0;
+    for (int src = 0; src < h->world; ++src) {
+        if (src == h->rank) my_start = n_recv;
+        n_recv += h->h_cnt[(int64_t)src * h->world + d];
+    }
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // one counter per rank -> offsets of the all-gather-v
 int gather_counts(amira_gmg *h, std::vector<int64_t> &off) {
@@ -645,34 +668,121 @@ int gather_counts(amira_gmg *h, std::vector<int64_t> &off) {
     return AMIRA_OK;
 }
 
+// all-gather-v of merged records: through the peer windows every rank copies its block straight into
+// every other rank's window (copy engines over NVLink) and a barrier publishes them; otherwise NCCL
+int publish_to_all(amira_gmg *h, bool p2p, const void *mine, int64_t n_mine, size_t elem, size_t win_off,
+                   const std::vector<int64_t> &g_off, void *fallback_recv) {
+    if (p2p) {
+        for (int q = 0; q < h->world; ++q) {
+            const int p = (h->rank + q) % h->world;  // staggered start: not everybody hits rank 0 first
+            char *dst = (char *)comm_window(h->comm, p) + win_off + (size_t)g_off[h->rank] * elem;
+            if (n_mine) AMIRA_CUDA(cudaMemcpyAsync(dst, mine, (size_t)n_mine * elem, cudaMemcpyDefault, h->stream));
+        }
+        return AMIRA_OK;
+    }
+    return comm_allgatherv(h->comm, mine, n_mine, fallback_recv, g_off.data(), elem, h->stream);
+}
+
+// AMIRA_SHARD_TRACE=1: per-step device times of the merge on stderr (developer aid)
+struct MergeTrace {
+    amira_gmg *h;
+    bool on;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    explicit MergeTrace(amira_gmg *h_) : h(h_), on(getenv("AMIRA_SHARD_TRACE") != nullptr) { mark("start"); }
+    void mark(const char *name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, h->stream);
+        marks.push_back({name, e});
+    }
+    ~MergeTrace() {
+        if (!on) return;
+        cudaStreamSynchronize(h->stream);
+        std::string line = "[merge rank " + std::to_string(h->rank) + "]";
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            char buf[96];
+            snprintf(buf, sizeof(buf), " %s=%.3f", marks[i].first, ms);
+            line += buf;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (auto &m : marks) cudaEventDestroy(m.second);
+    }
+};
+
 int sharded_merge(amira_gmg *h) {
     Phase ph(h, AMIRA_PH_EXCHANGE);
-    const int world = h->world, k = h->k;
+    MergeTrace tr(h);
+    const int world = h->world, k = h->k, me = h->rank;
     cudaStream_t st = h->stream;
     const int tgrid_n = std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16);
     const int tgrid_e = std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16);
     const long long call_base = h->first_call_global;
     AMIRA_TRY(h->x_cnt.reserve(sizeof(unsigned long long) * (2 * MAX_WORLD + (size_t)world * world + 8)));
     unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
-    const long long *d_off = (const long long *)(d_cnt + MAX_WORLD);
     std::vector<int64_t> send_off, recv_off, g_off;
     const size_t key_bytes = sizeof(int32_t) * (size_t)k;
+    bool p2p = comm_p2p(h->comm);
 
     // ---- nodes: route one record per locally-unique gene-mer to its owner
     AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, st));
-    LAUNCH(h, k_node_route<false>, tgrid_n, 256, h->nview, h->ids, k, world, call_base, d_cnt, nullptr, nullptr, nullptr);
+    NodeDst ndst;
+    memset(&ndst, 0, sizeof(ndst));
+    LAUNCH(h, k_node_route<false>, tgrid_n, 256, h->nview, h->ids, k, world, call_base, d_cnt, ndst);
     AMIRA_TRY(exchange_counts(h, send_off, recv_off));
+    tr.mark("n_count");
     const int64_t Nl = send_off[world], Nr = recv_off[world];
-    AMIRA_TRY(h->x_skey.reserve(key_bytes * std::max<int64_t>(Nl, 1)));
-    AMIRA_TRY(h->x_smeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nl, 1)));
-    AMIRA_TRY(h->x_rkey.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
-    AMIRA_TRY(h->x_rmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
+    int64_t nr_max = 0, nl_sum = 0;
+    for (int d = 0; d < world; ++d) {
+        int64_t n, my;
+        owner_layout(h, d, n, my);
+        nr_max = std::max(nr_max, n);
+        nl_sum += n;
+    }
+    // window layout (identical on every rank): [a2a keys | a2a meta | merged keys | merged meta]; the
+    // merged regions are sized for the worst case (nothing merges) so the window is mapped once
+    const size_t w_meta = align256(key_bytes * nr_max), w_gkey = w_meta + align256(sizeof(NodeRec) * nr_max);
+    const size_t w_gmeta = w_gkey + align256(key_bytes * nl_sum), w_end = w_gmeta + align256(sizeof(NodeRec) * nl_sum);
+    if (p2p) {
+        AMIRA_TRY(comm_window_ensure(h->comm, w_end, st));
+        p2p = comm_p2p(h->comm);
+    }
+    const int32_t *r_key;
+    const NodeRec *r_meta;
+    if (p2p) {
+        for (int d = 0; d < world; ++d) {
+            int64_t n, my;
+            owner_layout(h, d, n, my);
+            char *w = (char *)comm_window(h->comm, d);
+            ndst.key[d] = (int32_t *)w;
+            ndst.meta[d] = (NodeRec *)(w + w_meta);
+            ndst.start[d] = my;
+        }
+        LAUNCH(h, k_node_route<true>, tgrid_n, 256, h->nview, h->ids, k, world, call_base, d_cnt, ndst);
+        AMIRA_TRY(comm_barrier(h->comm, st));
+        r_key = (const int32_t *)comm_window(h->comm, me);
+        r_meta = (const NodeRec *)((const char *)comm_window(h->comm, me) + w_meta);
+    } else {
+        AMIRA_TRY(h->x_skey.reserve(key_bytes * std::max<int64_t>(Nl, 1)));
+        AMIRA_TRY(h->x_smeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nl, 1)));
+        AMIRA_TRY(h->x_rkey.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
+        AMIRA_TRY(h->x_rmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
+        for (int d = 0; d < world; ++d) {
+            ndst.key[d] = h->x_skey.as<int32_t>();
+            ndst.meta[d] = h->x_smeta.as<NodeRec>();
+            ndst.start[d] = send_off[d];
+        }
+        LAUNCH(h, k_node_route<true>, tgrid_n, 256, h->nview, h->ids, k, world, call_base, d_cnt, ndst);
+        AMIRA_TRY(comm_alltoallv(h->comm, h->x_skey.p, send_off.data(), h->x_rkey.p, recv_off.data(), key_bytes, st));
+        AMIRA_TRY(comm_alltoallv(h->comm, h->x_smeta.p, send_off.data(), h->x_rmeta.p, recv_off.data(), sizeof(NodeRec), st));
+        r_key = h->x_rkey.as<int32_t>();
+        r_meta = h->x_rmeta.as<NodeRec>();
+    }
+    tr.mark("n_a2a");
     AMIRA_TRY(h->x_rkey2.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
     AMIRA_TRY(h->x_rmeta2.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
-    LAUNCH(h, k_node_route<true>, tgrid_n, 256, h->nview, h->ids, k, world, call_base, d_cnt, d_off,
-           h->x_skey.as<int32_t>(), h->x_smeta.as<NodeRec>());
-    AMIRA_TRY(comm_alltoallv(h->comm, h->x_skey.p, send_off.data(), h->x_rkey.p, recv_off.data(), key_bytes, st));
-    AMIRA_TRY(comm_alltoallv(h->comm, h->x_smeta.p, send_off.data(), h->x_rmeta.p, recv_off.data(), sizeof(NodeRec), st));
 
     // ---- owner merge: records in first-position order into a table (sum of counts, earliest record)
     const int64_t sort_cap = std::max<int64_t>(Nr, 1);
@@ -691,11 +801,11 @@ int sharded_merge(amira_gmg *h) {
     P.k = k;
     P.status = h->d_status.as<int>();
     if (Nr > 0) {
-        LAUNCH(h, k_rec_ord_keys, grid_for(Nr, 256), 256, h->x_rmeta.as<NodeRec>(), (long long)Nr,
-               h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
+        LAUNCH(h, k_rec_ord_keys, grid_for(Nr, 256), 256, r_meta, (long long)Nr, h->x_sortk.as<unsigned long long>(),
+               h->x_sorti.as<unsigned int>());
         AMIRA_TRY(sort_by_ord(h, Nr));
-        LAUNCH(h, k_gather_node_recs, grid_for(Nr, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_rkey.as<int32_t>(),
-               h->x_rmeta.as<NodeRec>(), k, (long long)Nr, h->x_rkey2.as<int32_t>(), h->x_rmeta2.as<NodeRec>());
+        LAUNCH(h, k_gather_node_recs, grid_for(Nr, 256), 256, h->x_sorti2.as<unsigned int>(), r_key, r_meta, k,
+               (long long)Nr, h->x_rkey2.as<int32_t>(), h->x_rmeta2.as<NodeRec>());
         P.ids = h->x_rkey2.as<int32_t>();
         P.ntab = h->x_tab.as<NodeSlot>();
         P.ncap = (unsigned int)mcap;
@@ -705,15 +815,29 @@ int sharded_merge(amira_gmg *h) {
                h->x_mmeta.as<NodeRec>());
     }
     AMIRA_TRY(gather_counts(h, g_off));
+    tr.mark("n_merge");
     const int64_t Nm = g_off[h->rank + 1] - g_off[h->rank], Ng = g_off[world];
     if (Ng >= 0x7FFFFFF0ll) {
         set_error("too many nodes for int32 node indices");
         return AMIRA_E_ARG;
     }
-    AMIRA_TRY(h->x_gkey.reserve(key_bytes * std::max<int64_t>(Ng, 1)));
-    AMIRA_TRY(h->x_gmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Ng, 1)));
-    AMIRA_TRY(comm_allgatherv(h->comm, h->x_mkey.p, Nm, h->x_gkey.p, g_off.data(), key_bytes, st));
-    AMIRA_TRY(comm_allgatherv(h->comm, h->x_mmeta.p, Nm, h->x_gmeta.p, g_off.data(), sizeof(NodeRec), st));
+    const int32_t *g_key;
+    const NodeRec *g_meta;
+    if (p2p) {
+        AMIRA_TRY(publish_to_all(h, true, h->x_mkey.p, Nm, key_bytes, w_gkey, g_off, nullptr));
+        AMIRA_TRY(publish_to_all(h, true, h->x_mmeta.p, Nm, sizeof(NodeRec), w_gmeta, g_off, nullptr));
+        AMIRA_TRY(comm_barrier(h->comm, st));
+        g_key = (const int32_t *)((const char *)comm_window(h->comm, me) + w_gkey);
+        g_meta = (const NodeRec *)((const char *)comm_window(h->comm, me) + w_gmeta);
+    } else {
+        AMIRA_TRY(h->x_gkey.reserve(key_bytes * std::max<int64_t>(Ng, 1)));
+        AMIRA_TRY(h->x_gmeta.reserve(sizeof(NodeRec) * std::max<int64_t>(Ng, 1)));
+        AMIRA_TRY(publish_to_all(h, false, h->x_mkey.p, Nm, key_bytes, 0, g_off, h->x_gkey.p));
+        AMIRA_TRY(publish_to_all(h, false, h->x_mmeta.p, Nm, sizeof(NodeRec), 0, g_off, h->x_gmeta.p));
+        g_key = h->x_gkey.as<int32_t>();
+        g_meta = h->x_gmeta.as<NodeRec>();
+    }
+    tr.mark("n_allgather");
 
     // ---- global node arrays in upstream's insertion order (= first global position)
     AMIRA_TRY(h->node_key.reserve(key_bytes * std::max<int64_t>(1, Ng)));
@@ -729,11 +853,10 @@ int sharded_merge(amira_gmg *h) {
         AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * Ng));
         AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * Ng));
         AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * Ng));
-        LAUNCH(h, k_rec_ord_keys, grid_for(Ng, 256), 256, h->x_gmeta.as<NodeRec>(), (long long)Ng,
+        LAUNCH(h, k_rec_ord_keys, grid_for(Ng, 256), 256, g_meta, (long long)Ng,
                h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
         AMIRA_TRY(sort_by_ord(h, Ng));
-        LAUNCH(h, k_finalize_nodes, grid_for(Ng, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_gkey.as<int32_t>(),
-               h->x_gmeta.as<NodeRec>(), k, (long long)Ng, h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
+        LAUNCH(h, k_finalize_nodes, grid_for(Ng, 256), 256, h->x_sorti2.as<unsigned int>(), g_key, g_meta, k, (long long)Ng, h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
                h->node_dir.as<int8_t>(), h->parent.as<int32_t>());
         // lookup table over the global nodes; local slots -> global node indices
         mcap = std::min<int64_t>(2 * Ng + 1024, 0x7FFFFFF0ll);
@@ -743,34 +866,78 @@ int sharded_merge(amira_gmg *h) {
         P.ntab = h->x_tab.as<NodeSlot>();
         P.ncap = (unsigned int)mcap;
         LAUNCH(h, k_insert_records, grid_for(Ng, 256), 256, P, (long long)Ng, nullptr);
-        LAUNCH(h, k_local_to_global, tgrid_n, 256, h->nview, h->x_skey.as<int32_t>(), P, h->cov_local.as<uint32_t>());
+        LAUNCH(h, k_local_to_global, tgrid_n, 256, h->nview, h->ids, P, h->cov_local.as<uint32_t>());
     }
 
+    tr.mark("n_global");
     // ---- edges: one record per locally-unique undirected adjacency, keyed on global node indices
     AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, st));
-    LAUNCH(h, k_edge_route<false>, tgrid_e, 256, h->eview, h->nview, world, call_base, d_cnt, nullptr, nullptr);
+    EdgeDst edst;
+    memset(&edst, 0, sizeof(edst));
+    LAUNCH(h, k_edge_route<false>, tgrid_e, 256, h->eview, h->nview, world, call_base, d_cnt, edst);
     AMIRA_TRY(exchange_counts(h, send_off, recv_off));
+    tr.mark("e_count");
     const int64_t El = send_off[world], Er = recv_off[world];
-    AMIRA_TRY(h->x_sedge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(El, 1)));
-    AMIRA_TRY(h->x_redge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Er, 1)));
+    int64_t er_max = 0, el_sum = 0;
+    for (int d = 0; d < world; ++d) {
+        int64_t n, my;
+        owner_layout(h, d, n, my);
+        er_max = std::max(er_max, n);
+        el_sum += n;
+    }
+    const size_t w_gedge = align256(sizeof(EdgeSlot) * er_max), w_eend = w_gedge + align256(sizeof(EdgeSlot) * el_sum);
+    if (p2p) {
+        AMIRA_TRY(comm_window_ensure(h->comm, w_eend, st));
+        p2p = comm_p2p(h->comm);
+    }
+    const EdgeSlot *r_edge;
+    if (p2p) {
+        for (int d = 0; d < world; ++d) {
+            int64_t n, my;
+            owner_layout(h, d, n, my);
+            edst.rec[d] = (EdgeSlot *)comm_window(h->comm, d);
+            edst.start[d] = my;
+        }
+        LAUNCH(h, k_edge_route<true>, tgrid_e, 256, h->eview, h->nview, world, call_base, d_cnt, edst);
+        AMIRA_TRY(comm_barrier(h->comm, st));
+        r_edge = (const EdgeSlot *)comm_window(h->comm, me);
+    } else {
+        AMIRA_TRY(h->x_sedge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(El, 1)));
+        AMIRA_TRY(h->x_redge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Er, 1)));
+        for (int d = 0; d < world; ++d) {
+            edst.rec[d] = h->x_sedge.as<EdgeSlot>();
+            edst.start[d] = send_off[d];
+        }
+        LAUNCH(h, k_edge_route<true>, tgrid_e, 256, h->eview, h->nview, world, call_base, d_cnt, edst);
+        AMIRA_TRY(comm_alltoallv(h->comm, h->x_sedge.p, send_off.data(), h->x_redge.p, recv_off.data(), sizeof(EdgeSlot), st));
+        r_edge = h->x_redge.as<EdgeSlot>();
+    }
+    tr.mark("e_a2a");
     AMIRA_TRY(h->x_medge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Er, 1)));
-    LAUNCH(h, k_edge_route<true>, tgrid_e, 256, h->eview, h->nview, world, call_base, d_cnt, d_off,
-           h->x_sedge.as<EdgeSlot>());
-    AMIRA_TRY(comm_alltoallv(h->comm, h->x_sedge.p, send_off.data(), h->x_redge.p, recv_off.data(), sizeof(EdgeSlot), st));
     const int64_t mecap = std::min<int64_t>(2 * Er + 1024, 0x7FFFFFF0ll);
     AMIRA_TRY(h->x_etab.reserve(sizeof(EdgeSlot) * mecap));
     AMIRA_CUDA(cudaMemsetAsync(h->x_etab.p, 0xFF, sizeof(EdgeSlot) * mecap, st));
     AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
     if (Er > 0) {
-        LAUNCH(h, k_merge_edges, grid_for(Er, 256), 256, h->x_redge.as<EdgeSlot>(), (long long)Er, h->x_etab.as<EdgeSlot>(),
+        LAUNCH(h, k_merge_edges, grid_for(Er, 256), 256, r_edge, (long long)Er, h->x_etab.as<EdgeSlot>(),
                (unsigned int)mecap, h->d_status.as<int>());
         LAUNCH(h, k_pack_merged_edges, std::min<int>(grid_for(mecap, 256), h->n_sm * 16), 256, h->x_etab.as<EdgeSlot>(),
                (unsigned int)mecap, d_cnt, h->x_medge.as<EdgeSlot>());
     }
     AMIRA_TRY(gather_counts(h, g_off));
+    tr.mark("e_merge");
     const int64_t Em = g_off[h->rank + 1] - g_off[h->rank], Eg = g_off[world];
-    AMIRA_TRY(h->x_gedge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Eg, 1)));
-    AMIRA_TRY(comm_allgatherv(h->comm, h->x_medge.p, Em, h->x_gedge.p, g_off.data(), sizeof(EdgeSlot), st));
+    const EdgeSlot *g_edge;
+    if (p2p) {
+        AMIRA_TRY(publish_to_all(h, true, h->x_medge.p, Em, sizeof(EdgeSlot), w_gedge, g_off, nullptr));
+        AMIRA_TRY(comm_barrier(h->comm, st));
+        g_edge = (const EdgeSlot *)((const char *)comm_window(h->comm, me) + w_gedge);
+    } else {
+        AMIRA_TRY(h->x_gedge.reserve(sizeof(EdgeSlot) * std::max<int64_t>(Eg, 1)));
+        AMIRA_TRY(publish_to_all(h, false, h->x_medge.p, Em, sizeof(EdgeSlot), 0, g_off, h->x_gedge.p));
+        g_edge = h->x_gedge.as<EdgeSlot>();
+    }
+    tr.mark("e_allgather");
     int64_t E_dir = 0;
     AMIRA_TRY(h->x_fan.reserve(sizeof(int) * (Eg + 2)));
     if (Eg > 0) {
@@ -778,11 +945,11 @@ int sharded_merge(amira_gmg *h) {
         AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * Eg));
         AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * Eg));
         AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * Eg));
-        LAUNCH(h, k_edge_ord_keys, grid_for(Eg, 256), 256, h->x_gedge.as<EdgeSlot>(), (long long)Eg,
+        LAUNCH(h, k_edge_ord_keys, grid_for(Eg, 256), 256, g_edge, (long long)Eg,
                h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
         AMIRA_TRY(sort_by_ord(h, Eg));
-        LAUNCH(h, k_edge_fanout, grid_for(Eg + 1, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_gedge.as<EdgeSlot>(),
-               (long long)Eg, h->x_fan.as<int>());
+        LAUNCH(h, k_edge_fanout, grid_for(Eg + 1, 256), 256, h->x_sorti2.as<unsigned int>(), g_edge, (long long)Eg,
+               h->x_fan.as<int>());
         AMIRA_TRY(exclusive_sum_inplace(h, h->x_fan.as<int>(), Eg + 1));
         int e_dir32 = 0;
         AMIRA_CUDA(cudaMemcpyAsync(&e_dir32, h->x_fan.as<int>() + Eg, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -800,10 +967,10 @@ int sharded_merge(amira_gmg *h) {
     AMIRA_TRY(h->e_sd.reserve(E_dir + 1));
     AMIRA_TRY(h->e_td.reserve(E_dir + 1));
     AMIRA_TRY(h->e_cov.reserve(sizeof(uint32_t) * (E_dir + 1)));
-    if (Eg > 0)
-        LAUNCH(h, k_emit_edges_sorted, grid_for(Eg, 256), 256, h->x_sorti2.as<unsigned int>(), h->x_gedge.as<EdgeSlot>(),
-               h->x_fan.as<int>(), (long long)Eg, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
-               h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->parent.as<int32_t>());
+    // the directed edge arrays (+ union-find) are emitted on the second stream, beside the per-read passes
+    h->sh_Eg = Eg;
+    h->sh_gedge = g_edge;
+    tr.mark("e_global");
     h->n_nodes = Ng;
     h->n_edges = E_dir;
     h->prev_nodes = Nl;
@@ -1053,6 +1220,7 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
             r_all += h->h_cnt[2 * p];
             g_all += h->h_cnt[2 * p + 1];
         }
+        h->calls_global = g_all;
         if (r_all >= 0x7FFFFFF0ll || g_all >= (1ll << (P_BITS - 1))) {
             set_error("global read set too large (%lld reads, %lld calls)", r_all, g_all);
             return h->last_status = AMIRA_E_ARG;

@@ -31,18 +31,52 @@ __device__ __forceinline__ int owner_of(unsigned long long h, int world) {
     return (int)((((h >> 20) & 0xFFFFFull) * (unsigned long long)world) >> 20);
 }
 
+// position in the per-destination send range for every active lane: lanes of a warp that go to the same
+// destination share one atomicAdd (a per-record atomic on `world` counters serialises at L2)
+__device__ __forceinline__ long long reserve_for_dest(unsigned long long *counts, int d) {
+    const unsigned int peers = __match_any_sync(__activemask(), d);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&counts[d], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return (long long)base + __popc(peers & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ long long reserve_one(unsigned long long *counter) {
+    const unsigned int peers = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return (long long)base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void load_canonical(const int32_t *ids, unsigned long long word, int k, int32_t *out) {
     const unsigned long long p = (word >> 1) & P_MASK;
     const int neg = (int)(word & 1ull);
     for (int j = 0; j < k; ++j) out[j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
 }
 
-// pass 1 / pass 2 over the local node table: count per owner, then scatter into the send buffer
+// Where the records for each owner go: with peer windows (CUDA IPC over NVLink) these are addresses
+// in the OWNER's memory, so the routing kernel is the dispatch -- no staging buffer, no send/recv;
+// without them they all point into the local send buffer of the NCCL all-to-all.
+struct NodeDst {
+    int32_t *key[MAX_WORLD];
+    NodeRec *meta[MAX_WORLD];
+    long long start[MAX_WORLD];  // first record index of this rank's block at that owner
+};
+struct EdgeDst {
+    EdgeSlot *rec[MAX_WORLD];
+    long long start[MAX_WORLD];
+};
+
+// pass 1 / pass 2 over the local node table: count per owner, then scatter to the owners
 template <bool SCATTER>
 __global__ void k_node_route(const NodeView nv, const int32_t *__restrict__ ids, int k,
                              int world, long long call_base, unsigned long long *__restrict__ counts,
-                             const long long *__restrict__ dest_off, int32_t *__restrict__ s_key,
-                             NodeRec *__restrict__ s_meta) {
+                             const NodeDst dst) {
     __shared__ unsigned int s_cnt[MAX_WORLD];
     if (!SCATTER) {
         for (int i = threadIdx.x; i < world; i += blockDim.x) s_cnt[i] = 0;
@@ -58,14 +92,14 @@ __global__ void k_node_route(const NodeView nv, const int32_t *__restrict__ ids,
         if (!SCATTER) {
             atomicAdd(&s_cnt[d], 1u);
         } else {
-            const long long i = dest_off[d] + (long long)atomicAdd(&counts[d], 1ull);
-            for (int j = 0; j < k; ++j) s_key[i * k + j] = key[j];
+            const long long i = dst.start[d] + reserve_for_dest(counts, d);
+            int32_t *kd = dst.key[d] + i * k;
+            for (int j = 0; j < k; ++j) kd[j] = key[j];
             NodeRec r;
             r.ord = ((unsigned long long)(call_base + (long long)((w >> 1) & P_MASK)) << 1) | (w & 1ull);
             r.cov = nv.c(s) + 1u;
             r.pad = 0;
-            s_meta[i] = r;
-            nv.a(s) = (unsigned int)i;
+            dst.meta[d][i] = r;
         }
     }
     if (!SCATTER) {
@@ -114,7 +148,7 @@ __global__ void k_pack_merged_nodes(const NodeSlot *__restrict__ tab, unsigned i
         const unsigned long long w = tab[s].word;
         if (w == EMPTY64) continue;
         const long long r = (long long)(((w >> 1) & P_MASK) / (unsigned long long)k);
-        const long long i = (long long)atomicAdd(counter, 1ull);
+        const long long i = reserve_one(counter);
         for (int j = 0; j < k; ++j) out_key[i * k + j] = keys[r * k + j];
         NodeRec o;
         o.ord = meta[r].ord;
@@ -163,14 +197,16 @@ __device__ __forceinline__ long long node_lookup(const BuildParams &P, const int
     return 0;
 }
 
-// local node table: aux (index into the send buffer) -> global node index; local coverage per global node
-__global__ void k_local_to_global(const NodeView nv, const int32_t *__restrict__ s_key, const BuildParams G,
+// local node table: slot -> global node index; local coverage per global node
+__global__ void k_local_to_global(const NodeView nv, const int32_t *__restrict__ ids, const BuildParams G,
                                   uint32_t *__restrict__ cov_local) {
     const unsigned int stride = gridDim.x * blockDim.x;
+    int32_t key[MAX_K];
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
-        if (nv.w(s) == EMPTY64) continue;
-        const long long i = nv.a(s);
-        const long long g = node_lookup(G, s_key + i * G.k);
+        const unsigned long long w = nv.w(s);
+        if (w == EMPTY64) continue;
+        load_canonical(ids, w, G.k, key);
+        const long long g = node_lookup(G, key);
         nv.a(s) = (unsigned int)g;
         cov_local[g] = nv.c(s) + 1u;
     }
@@ -192,8 +228,8 @@ __device__ __forceinline__ EdgeSlot global_edge_record(unsigned long long key, u
 }
 
 template <bool SCATTER>
-__global__ void k_edge_route(const EdgeView ev, const NodeView nv, int world, long long call_base, unsigned long long *__restrict__ counts,
-                             const long long *__restrict__ dest_off, EdgeSlot *__restrict__ s_edges) {
+__global__ void k_edge_route(const EdgeView ev, const NodeView nv, int world, long long call_base,
+                             unsigned long long *__restrict__ counts, const EdgeDst dst) {
     __shared__ unsigned int s_cnt[MAX_WORLD];
     if (!SCATTER) {
         for (int i = threadIdx.x; i < world; i += blockDim.x) s_cnt[i] = 0;
@@ -207,7 +243,7 @@ __global__ void k_edge_route(const EdgeView ev, const NodeView nv, int world, lo
         const EdgeSlot r = global_edge_record(ekey, eord, ecov, nv, call_base);
         const int d = owner_of(mix64(r.key), world);
         if (!SCATTER) atomicAdd(&s_cnt[d], 1u);
-        else s_edges[dest_off[d] + (long long)atomicAdd(&counts[d], 1ull)] = r;
+        else dst.rec[d][dst.start[d] + reserve_for_dest(counts, d)] = r;
     }
     if (!SCATTER) {
         __syncthreads();
@@ -245,7 +281,7 @@ __global__ void k_pack_merged_edges(const EdgeSlot *__restrict__ tab, unsigned i
         EdgeSlot e = tab[s];
         if (e.key == EMPTY64) continue;
         e.cov += 1u;   // counts from 0xFFFFFFFF: the sum of the merged pair counts
-        out[atomicAdd(counter, 1ull)] = e;
+        out[reserve_one(counter)] = e;
     }
 }
 

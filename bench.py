@@ -45,6 +45,19 @@ BYTES_PER_GENE_MER = 13          # 4 id in + 4 node idx + 1 dire
 ATOMICS_PER_GENE_MER = 3         # 1 node update + 2 directed-edge updates
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the one JSON line, on the process's original stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -183,7 +196,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -398,7 +411,7 @@ def run_gpu(args):
         result["c2_isolate"] = {"workload": "BASELINE.json configs[1]: 50k reads x ~25 calls, 6k vocab, k=3",
                                 "gene_mers": w2, "ms_per_graph": ms2, "gene_mers_per_s": w2 / (ms2 * 1e-3)}
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        emit(result)
     dg.close()
     if world > 1:
         dist.destroy_process_group()
@@ -406,6 +419,12 @@ def run_gpu(args):
 
 
 def main():
+    # NCCL and friends print banners on stdout; the contract is ONE JSON line there, so everything else
+    # (including native code writing to fd 1) is sent to stderr and the line goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
