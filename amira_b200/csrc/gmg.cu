@@ -93,6 +93,7 @@ struct amira_gmg {
     int64_t first_read_global = 0, first_call_global = 0, calls_global = 0;
     int64_t sh_Eg = 0;               // merged undirected edge records of the current sharded build
     const EdgeSlot *sh_gedge = nullptr;
+    BuildParams local_P;             // parameters of the last k_insert_windows launch (the local tables)
     DevBuf x_cnt, x_skey, x_smeta, x_rkey, x_rmeta, x_rkey2, x_rmeta2, x_mkey, x_mmeta, x_gkey, x_gmeta, x_tab,
         x_sortk, x_sortk2, x_sorti, x_sorti2, x_sedge, x_redge, x_medge, x_gedge, x_etab, x_fan, cov_local;
     long long *h_cnt = nullptr;  // pinned, world*world + 4
@@ -333,6 +334,7 @@ int do_build(amira_gmg *h) {
                 P.ids_aligned = (reinterpret_cast<uintptr_t>(h->ids) & 15) == 0;
                 const int grid = (int)std::min<int64_t>((n_tiles + INS_WARPS - 1) / INS_WARPS,
                                                         (int64_t)h->n_sm * h->insert_ctas_per_sm);
+                h->local_P = P;
                 Phase phk(h, AMIRA_PH_INSERT_KERNEL);
 #define INSERT_KE(KK, NN, EE) LAUNCH(h, (k_insert_windows<KK, NN, EE>), grid, INS_THREADS, P)
 #define INSERT_K(KK)                                  \
@@ -673,11 +675,16 @@ int gather_counts(amira_gmg *h, std::vector<int64_t> &off) {
 int publish_to_all(amira_gmg *h, bool p2p, const void *mine, int64_t n_mine, size_t elem, size_t win_off,
                    const std::vector<int64_t> &g_off, void *fallback_recv) {
     if (p2p) {
+        PubDst dst;
+        memset(&dst, 0, sizeof(dst));
         for (int q = 0; q < h->world; ++q) {
-            const int p = (h->rank + q) % h->world;  // staggered start: not everybody hits rank 0 first
-            char *dst = (char *)comm_window(h->comm, p) + win_off + (size_t)g_off[h->rank] * elem;
-            if (n_mine) AMIRA_CUDA(cudaMemcpyAsync(dst, mine, (size_t)n_mine * elem, cudaMemcpyDefault, h->stream));
+            const int p = (h->rank + q) % h->world;  // staggered: not every rank stores to rank 0 first
+            dst.ptr[q] = (uint32_t *)((char *)comm_window(h->comm, p) + win_off + (size_t)g_off[h->rank] * elem);
         }
+        const long long n_words = (long long)((size_t)n_mine * elem / 4);
+        if (n_words > 0)
+            LAUNCH(h, k_publish, std::min<int>(grid_for(n_words, 256), h->n_sm * 16), 256, (const uint32_t *)mine, n_words,
+                   h->world, dst);
         return AMIRA_OK;
     }
     return comm_allgatherv(h->comm, mine, n_mine, fallback_recv, g_off.data(), elem, h->stream);
@@ -858,15 +865,10 @@ int sharded_merge(amira_gmg *h) {
         AMIRA_TRY(sort_by_ord(h, Ng));
         LAUNCH(h, k_finalize_nodes, grid_for(Ng, 256), 256, h->x_sorti2.as<unsigned int>(), g_key, g_meta, k, (long long)Ng, h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
                h->node_dir.as<int8_t>(), h->parent.as<int32_t>());
-        // lookup table over the global nodes; local slots -> global node indices
-        mcap = std::min<int64_t>(2 * Ng + 1024, 0x7FFFFFF0ll);
-        AMIRA_TRY(h->x_tab.reserve(sizeof(NodeSlot) * mcap));
-        AMIRA_CUDA(cudaMemsetAsync(h->x_tab.p, 0xFF, sizeof(NodeSlot) * mcap, st));
-        P.ids = h->node_key.as<int32_t>();
-        P.ntab = h->x_tab.as<NodeSlot>();
-        P.ncap = (unsigned int)mcap;
-        LAUNCH(h, k_insert_records, grid_for(Ng, 256), 256, P, (long long)Ng, nullptr);
-        LAUNCH(h, k_local_to_global, tgrid_n, 256, h->nview, h->ids, P, h->cov_local.as<uint32_t>());
+        // local slots -> global node indices: probe the rank's own node table with every global gene-mer
+        if (h->G > 0)
+            LAUNCH(h, k_global_to_local, grid_for(Ng, 256), 256, h->local_P, h->n16 ? 1 : 0, h->nview,
+                   h->node_key.as<int32_t>(), (long long)Ng, h->cov_local.as<uint32_t>());
     }
 
     tr.mark("n_global");

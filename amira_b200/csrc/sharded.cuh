@@ -212,6 +212,83 @@ __global__ void k_local_to_global(const NodeView nv, const int32_t *__restrict__
     }
 }
 
+// find-only probe of the LOCAL node table (any layout) for a canonical key; -1 if this rank never saw it.
+// Mirrors the probe sequences of node_insert16 / node_insert; after the insert kernel every key is published.
+__device__ __forceinline__ long long node_find_local(const BuildParams &L, bool n16, const int32_t *key) {
+    const int k = L.k, kb = L.key_bits;
+    if (kb > 0) {
+        const unsigned int bias = 1u << (kb - 1), lim = (1u << kb) - 1u;
+        unsigned long long klo = 0, khi = 0;
+        for (int i = 0; i < k; ++i) {
+            const unsigned int u = (unsigned int)key[i] + bias;
+            if (u >= lim) return -1;  // wider than any id of this rank's reads
+            khi = (khi << kb) | (klo >> (64 - kb));
+            klo = (klo << kb) | (unsigned long long)u;
+        }
+        const unsigned long long h = packed_hash(klo, khi);
+        if (n16) {
+            const unsigned int nb = L.ncap >> 1;
+            unsigned int b = (unsigned int)(((unsigned long long)(unsigned int)h * nb) >> 32);
+            const unsigned int top = (unsigned int)(((khi << 1) | (klo >> 63)) & ((1u << (64 - FP_SHIFT)) - 1u));
+            const unsigned long long keylow = klo & 0x7FFFFFFFFFFFFFFFull;
+            for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+                const NodeSlot16 *B = L.ntab16 + 2 * (size_t)b;
+                for (int i = 0; i < 2; ++i) {
+                    const unsigned long long cur = B[i].word;
+                    if (cur == EMPTY64) return -1;
+                    if ((unsigned int)(cur >> FP_SHIFT) == top && B[i].key == keylow) return 2ll * b + i;
+                }
+                if (++b == nb) b = 0;
+            }
+            return -1;
+        }
+        unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * L.ncap) >> 32);
+        for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+            const NodeSlot &S = L.ntab[s];
+            if (S.word == EMPTY64) return -1;
+            if (S.klo == klo && S.khi == khi) return s;
+            if (++s == L.ncap) s = 0;
+        }
+        return -1;
+    }
+    const unsigned long long h = canonical_hash(key, k, 0);
+    const unsigned int fp = (unsigned int)(h >> FP_SHIFT);
+    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * L.ncap) >> 32);
+    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+        const unsigned long long cur = L.ntab[s].word;
+        if (cur == EMPTY64) return -1;
+        if ((unsigned int)(cur >> FP_SHIFT) == fp && same_as_representative(L, key, 0, cur)) return s;
+        if (++s == L.ncap) s = 0;
+    }
+    return -1;
+}
+
+// global node j -> the local slot that holds the same gene-mer (if this rank saw it): the slot learns
+// its global node index, the global node its local coverage.  The probed table is the rank's own
+// L2-resident node table -- no table over the (much larger) global node set is ever built.
+__global__ void k_global_to_local(const BuildParams L, int n16, const NodeView nv, const int32_t *__restrict__ node_key,
+                                  long long n_global, uint32_t *__restrict__ cov_local) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_global) return;
+    const long long s = node_find_local(L, n16 != 0, node_key + j * L.k);
+    if (s < 0) return;
+    nv.a((unsigned int)s) = (unsigned int)j;
+    cov_local[j] = nv.c((unsigned int)s) + 1u;
+}
+
+// merged records -> the same offset in every rank's window (stores over NVLink, 4-byte granularity
+// because a record block may start at any multiple of 4 bytes)
+struct PubDst {
+    uint32_t *ptr[MAX_WORLD];
+};
+__global__ void k_publish(const uint32_t *__restrict__ src, long long n_words, int world, const PubDst dst) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        const uint32_t v = src[i];
+        for (int p = 0; p < world; ++p) dst.ptr[p][i] = v;
+    }
+}
+
 // ---- edges ----------------------------------------------------------------------------------------
 __device__ __forceinline__ EdgeSlot global_edge_record(unsigned long long key, unsigned long long ord, unsigned int cov,
                                                       const NodeView &nv, long long call_base) {
