@@ -31,6 +31,11 @@ struct amira_gmg {
     // (per-read lists -> node/read incidence); `cur` / `cur_temp` are what the launch helpers use.
     cudaStream_t stream2 = nullptr, cur = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Third stream: the per-read exports are copied out as soon as the per-read lists are final
+    // (ev_reads_ready: after the remap of a build, after the masking of a filter), i.e. while the
+    // incidence / adjacency / component passes of the same build are still running.
+    cudaStream_t stream_copy = nullptr;
+    cudaEvent_t ev_reads_ready = nullptr;
     DevBuf cub_temp2;
     DevBuf *cur_temp = nullptr;
     int n_sm = 148;
@@ -484,6 +489,7 @@ int do_build(amira_gmg *h) {
         Phase ph(h, AMIRA_PH_REMAP);
         LAUNCH(h, k_remap_windows, std::min<int>(grid_for(W, 256), h->n_sm * 32), 256, h->nview, h->win_node.as<int32_t>(), W);
     }
+    AMIRA_CUDA(cudaEventRecord(h->ev_reads_ready, h->stream));
     {
         Phase ph(h, AMIRA_PH_INCIDENCE);
         AMIRA_CUDA(cudaMemsetAsync(h->dups.p, 0, sizeof(uint32_t) * (N + 1), st));
@@ -592,6 +598,7 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
                h->has_pos ? h->win_start.as<int32_t>() : nullptr, h->has_pos ? h->win_end.as<int32_t>() : nullptr, W,
                h->to_correct.as<uint8_t>());
     }
+    AMIRA_CUDA(cudaEventRecord(h->ev_reads_ready, h->stream));
     std::swap(h->node_key, h->node_key2);
     std::swap(h->node_cov, h->node_cov2);
     std::swap(h->node_dir, h->node_dir2);
@@ -1045,6 +1052,8 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     }
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    AMIRA_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+    AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_reads_ready, cudaEventDisableTiming));
     h->cur = h->stream;
     h->cur_temp = &h->cub_temp;
     cudaDeviceProp prop;
@@ -1072,6 +1081,11 @@ void amira_gmg_destroy(amira_gmg *h) {
         cudaStreamSynchronize(h->stream2);
         cudaStreamDestroy(h->stream2);
     }
+    if (h->stream_copy) {
+        cudaStreamSynchronize(h->stream_copy);
+        cudaStreamDestroy(h->stream_copy);
+    }
+    if (h->ev_reads_ready) cudaEventDestroy(h->ev_reads_ready);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     h->cub_temp2.release();
@@ -1252,7 +1266,8 @@ int amira_gmg_sizes(amira_gmg *h, int64_t *n_nodes, int64_t *n_edges, int64_t *n
         set_error("sizes before a successful build");
         return AMIRA_E_STATE;
     }
-    AMIRA_TRY(finish_sizes(h));
+    // incidence / adjacency sizes are only known when the whole build has finished; the others earlier
+    if (n_incidence || n_fw || n_bw) AMIRA_TRY(finish_sizes(h));
     if (n_nodes) *n_nodes = h->n_nodes;
     if (n_edges) *n_edges = h->n_edges;
     if (n_windows) *n_windows = h->W;
@@ -1331,14 +1346,23 @@ int amira_gmg_export_reads(amira_gmg *h, int64_t *win_off, int32_t *node_idx, in
         return AMIRA_E_STATE;
     }
     const int64_t W = h->W, R = h->R;
-    AMIRA_TRY(d2h(h, win_off, h->win_off.p, sizeof(int64_t) * (R + 1)));
-    AMIRA_TRY(d2h(h, node_idx, h->win_node.p, sizeof(int32_t) * W));
-    AMIRA_TRY(d2h(h, dir, h->win_dir.p, W));
-    AMIRA_TRY(d2h(h, start, h->win_start.p, sizeof(int32_t) * W));
-    AMIRA_TRY(d2h(h, end, h->win_end.p, sizeof(int32_t) * W));
-    AMIRA_TRY(d2h(h, is_short, h->is_short.p, R));
-    AMIRA_TRY(d2h(h, to_correct, h->to_correct.p, R));
-    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    // the per-read lists are final before the rest of the build is: copy them out beside it
+    cudaStream_t cs = h->stream_copy;
+    AMIRA_CUDA(cudaStreamWaitEvent(cs, h->ev_reads_ready, 0));
+    struct {
+        void *dst;
+        const void *src;
+        size_t bytes;
+    } jobs[] = {{win_off, h->win_off.p, sizeof(int64_t) * (size_t)(R + 1)}, {node_idx, h->win_node.p, sizeof(int32_t) * (size_t)W},
+                {dir, h->win_dir.p, (size_t)W}, {start, h->win_start.p, sizeof(int32_t) * (size_t)W},
+                {end, h->win_end.p, sizeof(int32_t) * (size_t)W}, {is_short, h->is_short.p, (size_t)R},
+                {to_correct, h->to_correct.p, (size_t)R}};
+    for (auto &j : jobs) {
+        if (!j.dst || j.bytes == 0) continue;
+        AMIRA_CUDA(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, cs));
+        h->lib_launches++;
+    }
+    AMIRA_CUDA(cudaStreamSynchronize(cs));
     return AMIRA_OK;
 }
 

@@ -88,6 +88,13 @@ class DeviceGraph:
         names = ("nodes", "edges", "windows", "incidences", "fw", "bw", "short_reads")
         return dict(zip(names, (x.value for x in v)))
 
+    def sizes_early(self) -> dict:
+        """nodes / edges / windows / short reads: known before the incidence and adjacency passes finish"""
+        v = [C.c_int64() for _ in range(4)]
+        _lib.check(self._lib.amira_gmg_sizes(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), None, None, None,
+                                             C.byref(v[3])))
+        return dict(zip(("nodes", "edges", "windows", "short_reads"), (x.value for x in v)))
+
     def phase_ms(self) -> dict:
         out = {}
         for i, name in enumerate(_lib.PHASES):
@@ -133,8 +140,8 @@ class DeviceGraph:
 
     def arrays(self, out=None) -> dict:
         """export every graph array to host memory (numpy); `out` may supply preallocated buffers"""
-        s = self.sizes()
-        n, m, W, R, k = s["nodes"], s["edges"], s["windows"], self.R, self.k
+        early = self.sizes_early()
+        n, m, W, R, k = early["nodes"], early["edges"], early["windows"], self.R, self.k
 
         def buf(name, shape, dtype):
             if out is not None and name in out:
@@ -143,13 +150,6 @@ class DeviceGraph:
 
         a = {
             "k": np.int32(k),
-            "node_key": buf("node_key", (n, max(k, 0)), np.int32), "node_cov": buf("node_cov", n, np.uint32),
-            "node_dir": buf("node_dir", n, np.int8), "node_comp": buf("node_comp", n, np.uint32),
-            "node_reads_off": buf("node_reads_off", n + 1, np.int64), "node_reads": buf("node_reads", s["incidences"], np.int32),
-            "fw_off": buf("fw_off", n + 1, np.int64), "fw_edges": buf("fw_edges", s["fw"], np.int32),
-            "bw_off": buf("bw_off", n + 1, np.int64), "bw_edges": buf("bw_edges", s["bw"], np.int32),
-            "edge_src": buf("edge_src", m, np.int32), "edge_tgt": buf("edge_tgt", m, np.int32),
-            "edge_sd": buf("edge_sd", m, np.int8), "edge_td": buf("edge_td", m, np.int8), "edge_cov": buf("edge_cov", m, np.uint32),
             "win_off": buf("win_off", R + 1, np.int64), "win_node": buf("win_node", W, np.int32),
             "win_dir": buf("win_dir", W, np.int8), "is_short": buf("is_short", R, np.uint8),
             "to_correct": buf("to_correct", R, np.uint8),
@@ -157,14 +157,25 @@ class DeviceGraph:
         if self.has_pos:
             a["win_start"], a["win_end"] = buf("win_start", W, np.int32), buf("win_end", W, np.int32)
         L = self._lib
+        # per-read lists first: they are final before the rest of the build and are copied out beside it
+        _lib.check(L.amira_gmg_export_reads(self._h, _ptr(a["win_off"]), _ptr(a["win_node"]), _ptr(a["win_dir"]),
+                                            _ptr(a.get("win_start")), _ptr(a.get("win_end")), _ptr(a["is_short"]),
+                                            _ptr(a["to_correct"])))
+        s = self.sizes()
+        a.update({
+            "node_key": buf("node_key", (n, max(k, 0)), np.int32), "node_cov": buf("node_cov", n, np.uint32),
+            "node_dir": buf("node_dir", n, np.int8), "node_comp": buf("node_comp", n, np.uint32),
+            "node_reads_off": buf("node_reads_off", n + 1, np.int64), "node_reads": buf("node_reads", s["incidences"], np.int32),
+            "fw_off": buf("fw_off", n + 1, np.int64), "fw_edges": buf("fw_edges", s["fw"], np.int32),
+            "bw_off": buf("bw_off", n + 1, np.int64), "bw_edges": buf("bw_edges", s["bw"], np.int32),
+            "edge_src": buf("edge_src", m, np.int32), "edge_tgt": buf("edge_tgt", m, np.int32),
+            "edge_sd": buf("edge_sd", m, np.int8), "edge_td": buf("edge_td", m, np.int8), "edge_cov": buf("edge_cov", m, np.uint32),
+        })
         _lib.check(L.amira_gmg_export_nodes(self._h, _ptr(a["node_key"]), _ptr(a["node_cov"]), _ptr(a["node_dir"]),
                                             _ptr(a["node_comp"]), _ptr(a["node_reads_off"]), _ptr(a["node_reads"]),
                                             _ptr(a["fw_off"]), _ptr(a["fw_edges"]), _ptr(a["bw_off"]), _ptr(a["bw_edges"])))
         _lib.check(L.amira_gmg_export_edges(self._h, _ptr(a["edge_src"]), _ptr(a["edge_tgt"]), _ptr(a["edge_sd"]),
                                             _ptr(a["edge_td"]), _ptr(a["edge_cov"])))
-        _lib.check(L.amira_gmg_export_reads(self._h, _ptr(a["win_off"]), _ptr(a["win_node"]), _ptr(a["win_dir"]),
-                                            _ptr(a.get("win_start")), _ptr(a.get("win_end")), _ptr(a["is_short"]),
-                                            _ptr(a["to_correct"])))
         if not self.has_pos and out is None:
             a["win_start"] = np.full(W, -1, np.int32)
             a["win_end"] = np.full(W, -1, np.int32)

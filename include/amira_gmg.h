@@ -100,7 +100,9 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
 /* wait for the handle's stream; returns the deferred status of the last build / filter */
 int amira_gmg_sync(amira_gmg *h);
 
-/* sizes of the current (possibly filtered) graph */
+/* sizes of the current (possibly filtered) graph; any pointer may be NULL.  n_incidence / n_fw / n_bw
+ * wait for the whole build, the others are known as soon as the tables are (so that a caller can
+ * size and start the per-read export while the incidence / adjacency passes still run) */
 int amira_gmg_sizes(amira_gmg *h, int64_t *n_nodes, int64_t *n_edges, int64_t *n_windows,
                     int64_t *n_incidence, int64_t *n_fw, int64_t *n_bw, int64_t *n_short);
 
