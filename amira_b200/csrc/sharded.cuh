@@ -7,8 +7,8 @@
 //   nodes   one record per locally-unique gene-mer (canonical key, count, first global position,
 //           first direction) is routed to the owner rank hash(key) mod world with an all-to-all;
 //           the owner merges (sum of counts, minimum position) in a hash table; the merged
-//           records are all-gathered, sorted by first position = upstream's `_nodes` order, and
-//           every rank resolves its local nodes to global node indices through a lookup table.
+//           records are published to every rank, sorted by first position = upstream's `_nodes`
+//           order, and every rank maps the global nodes onto its local table by probing it.
 //   edges   the same with one record per locally-unique undirected adjacency, keyed on GLOBAL
 //           node indices (lo, hi, sd*td), carrying the pair count and the first pair event.
 //
@@ -169,47 +169,6 @@ __global__ void k_finalize_nodes(const unsigned int *__restrict__ perm, const in
     node_cov[i] = g_meta[s].cov;
     node_dir[i] = (g_meta[s].ord & 1ull) ? -1 : 1;
     parent[i] = (int32_t)i;
-}
-
-// find-only probe of a record table (every key looked up is present by construction)
-__device__ __forceinline__ long long node_lookup(const BuildParams &P, const int32_t *win) {
-    const unsigned int cap = P.ncap;
-    const int k = P.k;
-    const unsigned long long h = canonical_hash(win, k, 0);
-    unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
-    const unsigned int fp = (unsigned int)(h >> FP_SHIFT);
-    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
-        const unsigned long long cur = P.ntab[s].word;
-        if (cur == EMPTY64) break;
-        if ((unsigned int)(cur >> FP_SHIFT) == fp) {
-            const long long q = (long long)((cur >> 1) & P_MASK);
-            bool same = true;
-            for (int j = 0; j < k; ++j)
-                if (win[j] != P.ids[q + j]) {
-                    same = false;
-                    break;
-                }
-            if (same) return q / k;
-        }
-        if (++s == cap) s = 0;
-    }
-    P.status[ST_ERR] = AMIRA_E_STATE;
-    return 0;
-}
-
-// local node table: slot -> global node index; local coverage per global node
-__global__ void k_local_to_global(const NodeView nv, const int32_t *__restrict__ ids, const BuildParams G,
-                                  uint32_t *__restrict__ cov_local) {
-    const unsigned int stride = gridDim.x * blockDim.x;
-    int32_t key[MAX_K];
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
-        const unsigned long long w = nv.w(s);
-        if (w == EMPTY64) continue;
-        load_canonical(ids, w, G.k, key);
-        const long long g = node_lookup(G, key);
-        nv.a(s) = (unsigned int)g;
-        cov_local[g] = nv.c(s) + 1u;
-    }
 }
 
 // find-only probe of the LOCAL node table (any layout) for a canonical key; -1 if this rank never saw it.
