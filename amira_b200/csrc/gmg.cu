@@ -36,6 +36,13 @@ struct amira_gmg {
     // incidence / adjacency / component passes of the same build are still running.
     cudaStream_t stream_copy = nullptr;
     cudaEvent_t ev_reads_ready = nullptr;
+    // host input: the gene ids arrive in H2D_PIECES pieces on the copy stream; the insert kernel is
+    // launched once per piece, as soon as the piece after it (its halo) has landed
+    static constexpr int H2D_PIECES = 4;
+    cudaEvent_t ev_h2d[H2D_PIECES] = {};
+    cudaEvent_t ev_input_free = nullptr;
+    int64_t piece_end[H2D_PIECES] = {};  // call index where each piece ends; 0 pieces = input already resident
+    int n_pieces = 0;
     DevBuf cub_temp2;
     DevBuf *cur_temp = nullptr;
     int n_sm = 148;
@@ -283,6 +290,7 @@ int do_build(amira_gmg *h) {
         // ids).  k * id_bits <= 85: 16-byte slots whose identity is the key itself; <= 124: 32-byte
         // slots with the key published next to the claim word; else gene-mers are compared through ids.
         if (h->id_bits == 0 && G > 0) {
+            if (h->n_pieces) AMIRA_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[h->n_pieces - 1], 0));  // needs every id
             AMIRA_TRY(h->d_maxabs.reserve(sizeof(unsigned int)));
             AMIRA_CUDA(cudaMemsetAsync(h->d_maxabs.p, 0, sizeof(unsigned int), st));
             LAUNCH(h, k_max_abs, std::min<int>(grid_for(G, 256), h->n_sm * 16), 256, h->ids, G, h->d_maxabs.as<unsigned int>());
@@ -326,6 +334,7 @@ int do_build(amira_gmg *h) {
                 P.ids = h->ids; P.off = h->off; P.win_off = h->win_off.as<int64_t>();
                 P.tile_r0 = h->tile_r0.as<int32_t>(); P.ps = h->ps; P.pe = h->pe;
                 P.G = G; P.R = R; P.n_tiles = n_tiles; P.k = k;
+                P.tile_lo = 0; P.tile_hi = n_tiles;
                 P.ntab = h->ntab.as<NodeSlot>(); P.ntab16 = h->ntab.as<NodeSlot16>(); P.ncov = h->nview.cov;
                 P.ncap = h->ncap; P.etab = h->etab.as<EdgeSlot>(); P.etab16 = h->etab.as<EdgeSlot16>(); P.ecap = h->ecap;
                 P.win_node = h->win_node.as<int32_t>(); P.win_dir = h->win_dir.as<int8_t>();
@@ -337,8 +346,6 @@ int do_build(amira_gmg *h) {
                 P.key_bits = key_bits;
                 P.count_cov = h->world > 1;
                 P.ids_aligned = (reinterpret_cast<uintptr_t>(h->ids) & 15) == 0;
-                const int grid = (int)std::min<int64_t>((n_tiles + INS_WARPS - 1) / INS_WARPS,
-                                                        (int64_t)h->n_sm * h->insert_ctas_per_sm);
                 h->local_P = P;
                 Phase phk(h, AMIRA_PH_INSERT_KERNEL);
 #define INSERT_KE(KK, NN, EE) LAUNCH(h, (k_insert_windows<KK, NN, EE>), grid, INS_THREADS, P)
@@ -349,10 +356,27 @@ int do_build(amira_gmg *h) {
         else if (e16) INSERT_KE(KK, false, true);     \
         else INSERT_KE(KK, false, false);             \
     } while (0)
-                if (k == 3) INSERT_K(3);
-                else if (k == 5) INSERT_K(5);
-                else if (k == 7) INSERT_K(7);
-                else INSERT_K(0);
+                // one launch over everything, or (host input still streaming in) one launch per piece:
+                // piece i's chunks minus its last one, which needs the first ids of piece i+1
+                const int n_launch = std::max(1, h->n_pieces);
+                int64_t lo = 0;
+                for (int piece = 0; piece < n_launch; ++piece) {
+                    int64_t hi = n_tiles;
+                    if (h->n_pieces) {
+                        AMIRA_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[piece], 0));
+                        if (piece + 1 < n_launch) hi = std::max<int64_t>(lo, h->piece_end[piece] / INS_TILE - 1);
+                    }
+                    P.tile_lo = lo;
+                    P.tile_hi = hi;
+                    lo = hi;
+                    if (P.tile_hi <= P.tile_lo) continue;
+                    const int grid = (int)std::min<int64_t>((P.tile_hi - P.tile_lo + INS_WARPS - 1) / INS_WARPS,
+                                                            (int64_t)h->n_sm * h->insert_ctas_per_sm);
+                    if (k == 3) INSERT_K(3);
+                    else if (k == 5) INSERT_K(5);
+                    else if (k == 7) INSERT_K(7);
+                    else INSERT_K(0);
+                }
 #undef INSERT_K
 #undef INSERT_KE
                 if (n_tiles > 1) {
@@ -1054,6 +1078,8 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     AMIRA_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_reads_ready, cudaEventDisableTiming));
+    AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_input_free, cudaEventDisableTiming));
+    for (int i = 0; i < amira_gmg::H2D_PIECES; ++i) AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
     h->cur = h->stream;
     h->cur_temp = &h->cub_temp;
     cudaDeviceProp prop;
@@ -1086,6 +1112,9 @@ void amira_gmg_destroy(amira_gmg *h) {
         cudaStreamDestroy(h->stream_copy);
     }
     if (h->ev_reads_ready) cudaEventDestroy(h->ev_reads_ready);
+    if (h->ev_input_free) cudaEventDestroy(h->ev_input_free);
+    for (int i = 0; i < amira_gmg::H2D_PIECES; ++i)
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     h->cub_temp2.release();
@@ -1190,6 +1219,7 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
         return h->last_status = AMIRA_E_ARG;
     }
     h->G = G;
+    h->n_pieces = 0;
     if (input_on_device) {
         h->ids = signed_ids;
         h->off = read_off;
@@ -1199,9 +1229,26 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
         Phase ph(h, AMIRA_PH_H2D);
         AMIRA_TRY(h->d_ids.reserve(sizeof(int32_t) * std::max<int64_t>(G, 1) + 16));
         AMIRA_TRY(h->d_off.reserve(sizeof(int64_t) * (R + 1)));
-        if (G > 0) AMIRA_CUDA(cudaMemcpyAsync(h->d_ids.p, signed_ids, sizeof(int32_t) * G, cudaMemcpyHostToDevice, st));
+        // offsets first (the per-read pass needs only them), then the ids in pieces on the copy stream
         if (read_off) AMIRA_CUDA(cudaMemcpyAsync(h->d_off.p, read_off, sizeof(int64_t) * (R + 1), cudaMemcpyHostToDevice, st));
         else AMIRA_CUDA(cudaMemsetAsync(h->d_off.p, 0, sizeof(int64_t) * (R + 1), st));
+        h->n_pieces = 0;
+        if (G >= (int64_t)amira_gmg::H2D_PIECES * (1 << 20) && !h->has_pos) {
+            AMIRA_CUDA(cudaEventRecord(h->ev_input_free, st));  // earlier work on the main stream may still read d_ids
+            AMIRA_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_input_free, 0));
+            int64_t begin = 0;
+            for (int i = 0; i < amira_gmg::H2D_PIECES; ++i) {
+                int64_t end = (i + 1 == amira_gmg::H2D_PIECES) ? G : ((G * (i + 1) / amira_gmg::H2D_PIECES) / INS_TILE) * INS_TILE;
+                AMIRA_CUDA(cudaMemcpyAsync(h->d_ids.as<int32_t>() + begin, signed_ids + begin, sizeof(int32_t) * (end - begin),
+                                           cudaMemcpyHostToDevice, h->stream_copy));
+                AMIRA_CUDA(cudaEventRecord(h->ev_h2d[i], h->stream_copy));
+                h->piece_end[i] = end;
+                begin = end;
+            }
+            h->n_pieces = amira_gmg::H2D_PIECES;
+        } else if (G > 0) {
+            AMIRA_CUDA(cudaMemcpyAsync(h->d_ids.p, signed_ids, sizeof(int32_t) * G, cudaMemcpyHostToDevice, st));
+        }
         h->ids = h->d_ids.as<int32_t>();
         h->off = h->d_off.as<int64_t>();
         h->ps = h->pe = nullptr;

@@ -51,6 +51,7 @@ struct BuildParams {
     const int32_t *ps;
     const int32_t *pe;
     int64_t G, R, n_tiles;
+    int64_t tile_lo, tile_hi;  // chunks this launch covers (the host streams the ids in and launches per piece)
     int k;
     NodeSlot *ntab;      // 32-byte node slots (or NodeSlot16 *ntab16 + ncov when the gene-mers fit 85 bits)
     NodeSlot16 *ntab16;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParam
     const int kb = P.key_bits;  // bits per gene of the packed key (from the largest |id|), 0 = unpacked
     const bool packed = kb > 0;
     const int64_t n_warps = (int64_t)gridDim.x * INS_WARPS;
-    for (int64_t c = (int64_t)blockIdx.x * INS_WARPS + (threadIdx.x >> 5); c < P.n_tiles; c += n_warps) {
+    for (int64_t c = P.tile_lo + (int64_t)blockIdx.x * INS_WARPS + (threadIdx.x >> 5); c < P.tile_hi; c += n_warps) {
         const int64_t c0 = c * WC;
         const int len = (int)imin64(WC, P.G - c0);
         const int n_load = (int)imin64(len + k, P.G - c0);

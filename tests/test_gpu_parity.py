@@ -180,3 +180,15 @@ def test_gpu_python_class_on_a_fixture_scale_input():
     assert [n.get_node_coverage() for n in g.all_nodes()] == a2["node_cov"].tolist()
     assert len(g.get_edges()) == len(a2["edge_cov"])
     assert sorted(g.get_reads_to_correct()) == sorted(rid[i] for i in np.flatnonzero(a2["to_correct"]).tolist())
+
+
+def test_gpu_streamed_host_input(dg):
+    """host input large enough to arrive in pieces (one insert launch per piece) gives the oracle's graph"""
+    from amira_b200 import synth
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    ids, off = synth.generate(synth.CONFIGS["c5"], 0, 160000)
+    assert len(ids) >= 4 * (1 << 20)
+    for k in (5, 3):
+        dg.build(ids, off, k)
+        assert O.diff_arrays(dg.arrays(), c_oracle.COracleGraph(ids, off, k).arrays()) == [], k
