@@ -36,6 +36,9 @@ constexpr int INS_WARPS = INS_THREADS / 32;
 constexpr int WC = 128;        // calls per warp chunk
 constexpr int INS_TILE = WC;   // granularity of the chunk -> first read map
 constexpr int MAX_K = 64;
+#ifndef AMIRA_INS_MINB
+#define AMIRA_INS_MINB 8
+#endif
 constexpr int NR_STAGE = 30;   // reads of a chunk whose offsets are staged in shared memory
 constexpr unsigned int INVALID_VAL = 0xFFFFFFFFu;
 constexpr unsigned int MAX_PROBES = 1u << 15;
@@ -315,7 +318,7 @@ struct __align__(16) WarpStage {
 // it staged in shared memory.  K > 0: gene-mer size known at compile time (windows in registers).
 // N16 / E16: 16-byte node / edge slots.
 template <int K, bool N16, bool E16>
-__global__ void __launch_bounds__(INS_THREADS) k_insert_windows(const BuildParams P) {
+__global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(const BuildParams P) {
     __shared__ WarpStage s_stage[INS_WARPS];
     const int lane = threadIdx.x & 31;
     WarpStage &S = s_stage[threadIdx.x >> 5];
