@@ -68,10 +68,17 @@ def encode_reads(reads: dict, vocab: Vocabulary, positions: dict | None = None):
     off = np.zeros(len(reads) + 1, np.int64)
     np.cumsum(lens, out=off[1:])
     G = int(off[-1])
-    toks = [t.encode("utf-8") if isinstance(t, str) else _bad_token(t) for t in chain.from_iterable(reads.values())]
+    toks = list(chain.from_iterable(reads.values()))
+    try:
+        blob = "".join(toks).encode("utf-8")
+    except TypeError:
+        _bad_token(next(t for t in toks if not isinstance(t, str)))
     tok_off = np.zeros(G + 1, np.int64)
-    np.cumsum(np.fromiter((len(t) for t in toks), np.int64, G), out=tok_off[1:])
-    blob = b"".join(toks)
+    np.cumsum(np.fromiter(map(len, toks), np.int64, G), out=tok_off[1:])
+    if len(blob) != int(tok_off[-1]):          # non-ASCII gene names: byte lengths differ from str lengths
+        enc = [t.encode("utf-8") for t in toks]
+        np.cumsum(np.fromiter(map(len, enc), np.int64, G), out=tok_off[1:])
+        blob = b"".join(enc)
     vblob, voff = vocab.blob()
     ids = np.empty(G, np.int32)
     bad = C.c_int64(-1)
