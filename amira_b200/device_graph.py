@@ -138,8 +138,12 @@ class DeviceGraph:
         _lib.check(self._lib.amira_gmg_export_reads(self._h, None, _ptr(a["win_node"]), None, None, None, None, None))
         return a
 
-    def arrays(self, out=None) -> dict:
-        """export every graph array to host memory (numpy); `out` may supply preallocated buffers"""
+    def arrays(self, out=None, replicated=True) -> dict:
+        """export every graph array to host memory (numpy); `out` may supply preallocated buffers.
+
+        replicated=False (multi-GPU, ranks other than the one that collects the graph): skip the node /
+        edge tables every rank holds identically; export only what this rank owns -- its per-read
+        lists and its share of the node -> read incidence"""
         early = self.sizes_early()
         n, m, W, R, k = early["nodes"], early["edges"], early["windows"], self.R, self.k
 
@@ -162,6 +166,14 @@ class DeviceGraph:
                                             _ptr(a.get("win_start")), _ptr(a.get("win_end")), _ptr(a["is_short"]),
                                             _ptr(a["to_correct"])))
         s = self.sizes()
+        if not replicated:
+            a.update({"node_reads_off": buf("node_reads_off", n + 1, np.int64),
+                      "node_reads": buf("node_reads", s["incidences"], np.int32)})
+            _lib.check(L.amira_gmg_export_nodes(self._h, None, None, None, None, _ptr(a["node_reads_off"]),
+                                                _ptr(a["node_reads"]), None, None, None, None))
+            if n == 0:
+                a["node_reads_off"][:] = 0
+            return a
         a.update({
             "node_key": buf("node_key", (n, max(k, 0)), np.int32), "node_cov": buf("node_cov", n, np.uint32),
             "node_dir": buf("node_dir", n, np.int8), "node_comp": buf("node_comp", n, np.uint32),

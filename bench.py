@@ -307,16 +307,23 @@ def run_gpu(args):
     kernel_ms = sum(kern_ms) / len(kern_ms)
 
     # ---- end-to-end arm: host CSR in, host graph arrays out, through the C ABI ------------------
+    # multi-GPU: the node / edge tables are identical on every rank, so rank 0 collects them; every rank
+    # exports what it owns (its per-read lists and its share of the node -> read incidence)
+    replicated = rank == 0
     dg.build(h_ids.numpy(), h_off.numpy(), k)
-    out = dg.arrays()
+    out = dg.arrays(replicated=replicated)
     out_pinned = {n: pinned(a).numpy() for n, a in out.items() if isinstance(a, np.ndarray) and a.ndim >= 1 and
                   n not in ("win_start", "win_end")}
     d2h_bytes = int(sum(a.nbytes for a in out_pinned.values()))
     h2d_bytes = int(ids.nbytes + off.nbytes)
+    if world > 1:                                 # bytes per step of the whole job
+        tb = torch.tensor([h2d_bytes, d2h_bytes], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tb)
+        h2d_bytes, d2h_bytes = int(tb[0].item()), int(tb[1].item())
 
     def step_e2e():
         dg.build(h_ids.numpy(), h_off.numpy(), k)
-        dg.arrays(out=out_pinned)
+        dg.arrays(out=out_pinned, replicated=replicated)
 
     n_e2e = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -375,7 +382,9 @@ def run_gpu(args):
         "graph": {"gene_mers": W_all, "nodes": sizes["nodes"], "edges": sizes["edges"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / n_e2e, "steps": n_e2e,
-                "what": "pinned host CSR -> amira_gmg_build -> amira_gmg_export_{nodes,edges,reads} into pinned host arrays"},
+                "what": "pinned host CSR -> amira_gmg_build -> amira_gmg_export_{nodes,edges,reads} into pinned host arrays"
+                        + (" (every rank: its per-read lists and incidence share; rank 0: also the replicated node / edge "
+                           "tables; bytes are the job's total)" if n_gpus > 1 else "")},
         "gpu_launches": int(launches), "phases_ms": phases, "roofline": roofline, "clocks": clocks,
         "library": _lib.load().amira_version().decode(),
     }
