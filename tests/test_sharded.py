@@ -73,4 +73,4 @@ def test_sharded_build_matches_oracle_nccl(args):
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs at least 2 GPUs (run under gpurun --gpus 2)")
-    _run(min(n, 4) if "--uneven" not in args else 2, "--backend", "nccl", *args)
+    _run(min(n, 8) if "--uneven" not in args else 2, "--backend", "nccl", *args)
