@@ -275,12 +275,16 @@ int do_build(amira_gmg *h) {
     // unique counts, scaled by the call-count ratio, size the tables at ~50% load; a cold build uses
     // G/4 slots.  Either way an overflow is detected on the device and retried larger.
     int64_t ncap = std::max<int64_t>(4096, G / 4), ecap = std::max<int64_t>(4096, G / 4);
+    // Load factor: a warp waits for the longest probe sequence among its lanes, so the 16-byte tables run
+    // at ~30 % load (measured on the C5 shard: insert kernel 0.91 ms at 50 %, 0.78 ms at 30 %, 0.76 ms at
+    // 25 % -- although the tables then outgrow L2); the 32-byte layouts stay at 50 %.
+    const double nslack = h->n16 ? 3.2 : 2.0, eslack = (G < (1ll << ORD32_P_BITS)) ? 3.2 : 2.0;
     if (h->hint_nodes > 0) ncap = h->hint_nodes * 2 + 1024;
     else if (h->prev_G > 0 && G <= 4 * h->prev_G)
-        ncap = (int64_t)((double)h->prev_nodes * ((double)G / (double)h->prev_G) * 2.0) + 4096;
+        ncap = (int64_t)((double)h->prev_nodes * ((double)G / (double)h->prev_G) * nslack) + 4096;
     if (h->hint_edges > 0) ecap = h->hint_edges * 2 + 1024;
     else if (h->prev_G > 0 && G <= 4 * h->prev_G)
-        ecap = (int64_t)((double)h->prev_und_edges * ((double)G / (double)h->prev_G) * 2.0) + 4096;
+        ecap = (int64_t)((double)h->prev_und_edges * ((double)G / (double)h->prev_G) * eslack) + 4096;
     int key_bits = 0;
     bool n16 = false;
     const bool e16 = G < (1ll << ORD32_P_BITS) && !(h->force_layout & 2);
@@ -484,7 +488,11 @@ int do_build(amira_gmg *h) {
             Phase ph(h, AMIRA_PH_EMIT);
             LAUNCH(h, k_emit_edges, std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16), 256, h->eview, h->nview, bm_ea, bm_eb,
                    h->cnt_edge.as<int>(), h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
-                   h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->parent.as<int32_t>());
+                   h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), (int32_t *)nullptr);
+            // union-find in first-seen edge order rather than table order: measured 0.49 ms against 0.73 ms,
+            // and independent of where the hash happened to put the edges
+            LAUNCH(h, k_union_edges, grid_for(E, 256), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E,
+                   h->parent.as<int32_t>());
         }
         if (h->world > 1 && h->sh_Eg > 0) {
             Phase ph(h, AMIRA_PH_EMIT);

@@ -653,7 +653,7 @@ __global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
             e_src[idx] = src; e_tgt[idx] = tgt; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = cov;
             e_src[idx + 1] = tgt; e_tgt[idx + 1] = src; e_sd[idx + 1] = (int8_t)-td; e_td[idx + 1] = (int8_t)-sd;
             e_cov[idx + 1] = cov;
-            uf_union(parent, src, tgt);
+            if (parent) uf_union(parent, src, tgt);
         } else {
             // S == T: forward and reverse are the same Edge object, incremented twice per pair
             e_src[idx] = src; e_tgt[idx] = src; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = 2u * cov;
@@ -719,6 +719,15 @@ __global__ void k_adj_keys(const int32_t *__restrict__ e_src, const int8_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------
+// union-find over the emitted edges in first-seen order (each undirected adjacency once)
+__global__ void k_union_edges(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt, int64_t n_edges,
+                              int32_t *__restrict__ parent) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int s = e_src[e], t = e_tgt[e];
+    if (s < t) uf_union(parent, s, t);
+}
+
 // root of every node (read-only walk: the unions are over, trees are shallow thanks to the random
 // linking) and each component's first node (cmin starts at 0xFFFFFFFF)
 __global__ void k_cc_flatten(const int32_t *__restrict__ parent, int64_t n_nodes, unsigned int *__restrict__ cmin,
