@@ -53,6 +53,11 @@ struct amira_gmg {
     NodeView nview;
     EdgeView eview;
     DevBuf d_maxabs;
+    // the largest |id| of every build is measured on the second stream beside the insert kernel and
+    // picked up by the next build, so the key width follows the data in both directions
+    unsigned int *h_maxabs = nullptr;  // pinned
+    cudaEvent_t ev_maxabs = nullptr;
+    bool maxabs_pending = false;
 
     // input (owned copy or borrowed device pointers)
     DevBuf d_ids, d_off, d_ps, d_pe;
@@ -285,6 +290,16 @@ int do_build(amira_gmg *h) {
     if (h->hint_edges > 0) ecap = h->hint_edges * 2 + 1024;
     else if (h->prev_G > 0 && G <= 4 * h->prev_G)
         ecap = (int64_t)((double)h->prev_und_edges * ((double)G / (double)h->prev_G) * eslack) + 4096;
+    auto bits_for_ids = [](unsigned int max_abs) {
+        int b = 2;
+        while (b < 32 && ((1ull << (b - 1)) - 2) < (unsigned long long)max_abs) ++b;
+        return b;
+    };
+    if (h->maxabs_pending) {  // measured beside the previous build's insert kernel
+        AMIRA_CUDA(cudaEventSynchronize(h->ev_maxabs));
+        h->maxabs_pending = false;
+        if (h->id_bits != 0) h->id_bits = bits_for_ids(*h->h_maxabs);
+    }
     int key_bits = 0;
     bool n16 = false;
     const bool e16 = G < (1ll << ORD32_P_BITS) && !(h->force_layout & 2);
@@ -295,15 +310,13 @@ int do_build(amira_gmg *h) {
         // slots with the key published next to the claim word; else gene-mers are compared through ids.
         if (h->id_bits == 0 && G > 0) {
             if (h->n_pieces) AMIRA_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[h->n_pieces - 1], 0));  // needs every id
-            AMIRA_TRY(h->d_maxabs.reserve(sizeof(unsigned int)));
+            AMIRA_TRY(h->d_maxabs.reserve(2 * sizeof(unsigned int)));
             AMIRA_CUDA(cudaMemsetAsync(h->d_maxabs.p, 0, sizeof(unsigned int), st));
             LAUNCH(h, k_max_abs, std::min<int>(grid_for(G, 256), h->n_sm * 16), 256, h->ids, G, h->d_maxabs.as<unsigned int>());
             unsigned int max_abs = 0;
             AMIRA_CUDA(cudaMemcpyAsync(&max_abs, h->d_maxabs.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
             AMIRA_CUDA(cudaStreamSynchronize(st));
-            int b = 2;
-            while (b < 32 && ((1ull << (b - 1)) - 2) < (unsigned long long)max_abs) ++b;
-            h->id_bits = b;
+            h->id_bits = bits_for_ids(max_abs);
         }
         const int T = k * (h->id_bits ? h->id_bits : 32);
         n16 = T <= KEY16_BITS && h->id_bits < 32 && !(h->force_layout & 1);
@@ -383,6 +396,20 @@ int do_build(amira_gmg *h) {
                 }
 #undef INSERT_K
 #undef INSERT_KE
+                if (attempt == 0) {
+                    // this input's largest |id|, for the next build on the handle (second stream, beside the insert)
+                    AMIRA_TRY(h->d_maxabs.reserve(2 * sizeof(unsigned int)));  // [0]: synchronous measure, [1]: this one
+                    unsigned int *d_next = h->d_maxabs.as<unsigned int>() + 1;
+                    AMIRA_CUDA(cudaEventRecord(h->ev_fork, st));
+                    AMIRA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+                    if (h->n_pieces) AMIRA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_h2d[h->n_pieces - 1], 0));
+                    SideStream side(h);
+                    AMIRA_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), h->cur));
+                    LAUNCH(h, k_max_abs, std::min<int>(grid_for(G, 256), h->n_sm * 4), 256, h->ids, G, d_next);
+                    AMIRA_CUDA(cudaMemcpyAsync(h->h_maxabs, d_next, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->cur));
+                    AMIRA_CUDA(cudaEventRecord(h->ev_maxabs, h->cur));
+                    h->maxabs_pending = true;
+                }
                 if (n_tiles > 1) {
                     if (e16) LAUNCH(h, k_boundary_edges<true>, grid_for(n_tiles - 1, 256), 256, P);
                     else LAUNCH(h, k_boundary_edges<false>, grid_for(n_tiles - 1, 256), 256, P);
@@ -1099,6 +1126,8 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     AMIRA_TRY(h->d_status.reserve(sizeof(int) * ST_COUNT));
     AMIRA_TRY(h->d_sizes.reserve(sizeof(long long) * SZ_COUNT));
     AMIRA_TRY(h->d_nsel.reserve(sizeof(long long)));
+    AMIRA_CUDA(cudaMallocHost((void **)&h->h_maxabs, sizeof(unsigned int)));
+    AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_maxabs, cudaEventDisableTiming));
     AMIRA_CUDA(cudaMallocHost((void **)&h->h_status, sizeof(int) * ST_COUNT));
     AMIRA_CUDA(cudaMallocHost((void **)&h->h_sizes, sizeof(long long) * SZ_COUNT));
     for (int i = 0; i < AMIRA_PH_COUNT; ++i)
@@ -1141,6 +1170,8 @@ void amira_gmg_destroy(amira_gmg *h) {
     for (DevBuf *b : bufs) b->release();
     if (h->comm) comm_destroy(h->comm);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->h_maxabs) cudaFreeHost(h->h_maxabs);
+    if (h->ev_maxabs) cudaEventDestroy(h->ev_maxabs);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_sizes) cudaFreeHost(h->h_sizes);
     for (int i = 0; i < AMIRA_PH_COUNT; ++i)

@@ -192,3 +192,20 @@ def test_gpu_streamed_host_input(dg):
     for k in (5, 3):
         dg.build(ids, off, k)
         assert O.diff_arrays(dg.arrays(), c_oracle.COracleGraph(ids, off, k).arrays()) == [], k
+
+
+def test_gpu_key_width_follows_the_data_down_again():
+    """after an input with huge gene ids the handle goes back to the compact layout for small ids (timing aside,
+    the graphs must stay exact across the switches)"""
+    from amira_b200.device_graph import DeviceGraph
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    rng = np.random.default_rng(9)
+    off = np.arange(0, 6001, 30).astype(np.int64)
+    g = DeviceGraph(0)
+    for vmax in (300, 1_500_000_000, 300, 300, 70_000, 300):
+        ids = (rng.integers(1, vmax + 1, off[-1]) * rng.choice([-1, 1], off[-1])).astype(np.int32)
+        ids[:60] = np.tile(ids[:6], 10)
+        g.build(ids, off, 5)
+        assert O.diff_arrays(g.arrays(), c_oracle.COracleGraph(ids, off, 5).arrays()) == [], vmax
+    g.close()
