@@ -11,8 +11,9 @@ from .construct_graph import GeneMerGraph, bind_upstream
 from .construct_node import Node
 from .construct_read import Read
 from .device_graph import DeviceGraph
+from .encode import EncodedReads
 from .graph_utils import build_graph, build_multiprocessed_graph
 
-__all__ = ["GeneMerGraph", "bind_upstream", "build_graph", "build_multiprocessed_graph", "DeviceGraph",
+__all__ = ["GeneMerGraph", "bind_upstream", "build_graph", "build_multiprocessed_graph", "DeviceGraph", "EncodedReads",
            "Gene", "GeneMer", "Read", "Node", "Edge", "hashlib_hash"]
 __version__ = "0.1.0"

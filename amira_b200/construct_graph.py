@@ -73,6 +73,11 @@ class GeneMerGraph:
     _cls = _Classes
 
     def __init__(self, readDict, kmerSize, gene_positions=None, device=None):
+        # an encode.EncodedReads in place of the dict: the strings were parsed once, reuse the CSR
+        self._encoded = readDict if isinstance(readDict, encode.EncodedReads) else None
+        if self._encoded is not None:
+            gene_positions = self._encoded.positions if gene_positions is None else gene_positions
+            readDict = self._encoded.reads
         self._reads = readDict
         self._kmerSize = kmerSize
         self._minNodeCoverage = 1
@@ -98,6 +103,9 @@ class GeneMerGraph:
 
     # ------------------------------------------------------------------ device build
     def _encode(self):
+        if self._encoded is not None:
+            e = self._encoded
+            return e.vocab, e.ids, e.off, e.pos_start, e.pos_end
         reads = self._reads
         vocab = encode.Vocabulary(encode.collect_names(reads))
         positions = self._genePositions if self._genePositions else None
@@ -109,7 +117,10 @@ class GeneMerGraph:
         self._vocab = vocab
         h = _handle(self._device)
         h.owner = None
-        h.build(ids, off, int(self._kmerSize), ps, pe)
+        if self._encoded is not None and hasattr(h, "build_resident"):
+            h.build_resident(self._encoded, int(self._kmerSize), self._device)
+        else:
+            h.build(ids, off, int(self._kmerSize), ps, pe)
         arrays = h.arrays()
         h.owner = weakref.ref(self)
         self._materialise(arrays, vocab)

@@ -64,6 +64,11 @@ class DeviceGraph:
                                              int(on_device)))
         return self
 
+    def build_resident(self, encoded, k: int, device: int | None = None):
+        """build from an encode.EncodedReads whose CSR stays on the GPU between builds (k sweeps, rebuilds)"""
+        ids, off, ps, pe = encoded.device_csr(self.device if device is None else device)
+        return self.build(ids, off, k, ps, pe, on_device=True)
+
     def sync(self):
         _lib.check(self._lib.amira_gmg_sync(self._h))
 

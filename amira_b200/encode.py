@@ -109,3 +109,61 @@ def encode_reads(reads: dict, vocab: Vocabulary, positions: dict | None = None):
 
 def _bad_token(t):
     raise AttributeError("gene calls must be strings, got %r" % (t,))
+
+
+class EncodedReads:
+    """A read set encoded once: vocabulary + signed-id CSR (+ optional positions).
+
+    Amira rebuilds the graph of the same reads many times (k sweep in ``choose_kmer_size``,
+    amira/graph_utils.py:258-296; the ~10 rebuilds of ``__main__.py``).  Passing an ``EncodedReads`` to
+    ``GeneMerGraph`` in place of the read dict skips the string parsing, and ``device_csr()`` keeps the CSR
+    resident on the GPU between builds.  ``save`` / ``load`` are the binary form of upstream's gene-call
+    JSON (``process_pandora_json``, amira/pre_processing.py:44-63; ``write_pandora_gene_calls``,
+    amira/result_utils.py:1260-1264): an ``.npz`` with the CSR and a vocabulary / read-id sidecar."""
+
+    def __init__(self, reads: dict, positions: dict | None = None):
+        self.reads = reads
+        self.positions = positions if positions else None
+        self.read_ids = list(reads)
+        self.vocab = Vocabulary(collect_names(reads))
+        self.ids, self.off, self.pos_start, self.pos_end = encode_reads(reads, self.vocab, self.positions)
+        self._device = None
+
+    def __len__(self):
+        return len(self.read_ids)
+
+    def device_csr(self, device: int = 0):
+        """(ids, off, pos_start, pos_end) as CUDA tensors on `device`, uploaded once"""
+        if self._device is None or self._device[0] != device:
+            import torch
+            dev = torch.device("cuda", device)
+            t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+            self._device = (device, t(self.ids), t(self.off), t(self.pos_start), t(self.pos_end))
+            torch.cuda.synchronize(dev)
+        return self._device[1:]
+
+    def save(self, path: str):
+        extra = {} if self.pos_start is None else {"pos_start": self.pos_start, "pos_end": self.pos_end}
+        np.savez_compressed(path, ids=self.ids, off=self.off, vocab=np.array(self.vocab.names, dtype=object),
+                            read_ids=np.array(self.read_ids, dtype=object), **extra)
+
+    @classmethod
+    def load(cls, path: str):
+        z = np.load(path, allow_pickle=True)
+        self = cls.__new__(cls)
+        self.vocab = Vocabulary.__new__(Vocabulary)
+        self.vocab.names, self.vocab._blob = [str(n) for n in z["vocab"]], None
+        self.read_ids = [str(r) for r in z["read_ids"]]
+        self.ids, self.off = z["ids"].astype(np.int32), z["off"].astype(np.int64)
+        self.pos_start = z["pos_start"].astype(np.int32) if "pos_start" in z.files else None
+        self.pos_end = z["pos_end"].astype(np.int32) if "pos_end" in z.files else None
+        self._device = None
+        names = self.vocab.names
+        toks = [("+" if g > 0 else "-") + names[abs(g) - 1] for g in self.ids.tolist()]
+        off = self.off.tolist()
+        self.reads = {r: toks[off[i]:off[i + 1]] for i, r in enumerate(self.read_ids)}
+        self.positions = None
+        if self.pos_start is not None:
+            ps, pe = self.pos_start.tolist(), self.pos_end.tolist()
+            self.positions = {r: [(ps[j], pe[j]) for j in range(off[i], off[i + 1])] for i, r in enumerate(self.read_ids)}
+        return self

@@ -209,3 +209,14 @@ def test_gpu_key_width_follows_the_data_down_again():
         g.build(ids, off, 5)
         assert O.diff_arrays(g.arrays(), c_oracle.COracleGraph(ids, off, 5).arrays()) == [], vmax
     g.close()
+
+
+def test_gpu_k_sweep_on_resident_encoding():
+    """EncodedReads keeps the CSR on the device; a k sweep over it equals building from the dict each time"""
+    from amira_b200 import EncodedReads, GeneMerGraph, synth
+    from tests.graph_snapshot import snapshot
+    ids, off = synth.generate(synth.CONFIGS["c2"], 0, 800)
+    reads = synth.to_read_dict(ids, off, synth.vocabulary_names(synth.CONFIGS["c2"].vocab))
+    enc = EncodedReads(reads)
+    for k in (3, 5, 7):
+        assert snapshot(GeneMerGraph(enc, k)) == snapshot(GeneMerGraph(reads, k))

@@ -149,3 +149,23 @@ def test_bind_upstream_runs_upstream_methods_on_our_build(fake_device, golden_sm
     assert ours.get_nodes_containing("c") == theirs.get_nodes_containing("c")
     ours.filter_graph(2, 1), theirs.filter_graph(2, 1)
     assert snapshot(ours) == snapshot(theirs)
+
+
+def test_encoded_reads_reuse_and_binary_round_trip(fake_device, tmp_path, golden_small):
+    """one parse of the gene-call strings serves every k; the binary form round-trips to the same graph"""
+    from amira_b200 import EncodedReads
+    case = next(c for c in golden_small if not c.get("raises") and len(c["reads"]) >= 2 and c["positions"])
+    enc = EncodedReads(case["reads"], case["positions"])
+    a = snapshot(amira_b200.GeneMerGraph(enc, case["k"]))
+    assert a == snapshot(amira_b200.GeneMerGraph(case["reads"], case["k"], case["positions"])) == case["build"]
+    enc.save(str(tmp_path / "calls.npz"))
+    back = EncodedReads.load(str(tmp_path / "calls.npz"))
+    assert back.reads == {r: [("+" if t[0] == "+" else "-") + t[1:].replace(" ", "_") for t in v]
+                          for r, v in case["reads"].items()}
+    assert snapshot(amira_b200.GeneMerGraph(back, case["k"]))["node_hashes"] == a["node_hashes"]
+    for k in (1, 2, 3):                     # the sweep: same encoding, different gene-mer sizes
+        try:
+            g1, g2 = amira_b200.GeneMerGraph(enc, k), amira_b200.GeneMerGraph(case["reads"], k, case["positions"])
+        except AssertionError:
+            continue
+        assert snapshot(g1) == snapshot(g2)
