@@ -220,3 +220,20 @@ def test_gpu_k_sweep_on_resident_encoding():
     enc = EncodedReads(reads)
     for k in (3, 5, 7):
         assert snapshot(GeneMerGraph(enc, k)) == snapshot(GeneMerGraph(reads, k))
+
+
+def test_gpu_table_overflow_is_retried():
+    """capacity hints far too small: the device reports the overflow and the build is redone larger"""
+    from amira_b200 import synth
+    from amira_b200.device_graph import DeviceGraph
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    ids, off = synth.generate(synth.CONFIGS["c3"], 0, 20000)
+    ref = c_oracle.COracleGraph(ids, off, 3).arrays()
+    g = DeviceGraph(0)
+    for mask in (0, 3):                      # 16-byte bucketed tables, then the 32-byte ones
+        g.debug_layout(mask)
+        g.reserve(10, 10)
+        g.build(ids, off, 3)
+        assert O.diff_arrays(g.arrays(), ref) == [], mask
+    g.close()
