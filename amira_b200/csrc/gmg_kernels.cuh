@@ -169,7 +169,8 @@ __device__ __forceinline__ unsigned int node_insert(const BuildParams &P, const 
     const unsigned int cap = P.ncap;
     unsigned int s = (unsigned int)(((unsigned long long)(unsigned int)h * cap) >> 32);
     const unsigned int fp = (unsigned int)(mine >> FP_SHIFT);
-    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+    const unsigned int max_probe = min(MAX_PROBES, cap);
+    for (unsigned int probe = 0; probe < max_probe; ++probe) {
         unsigned long long cur, ca, sl, sh;
         load_node_slot(&P.ntab[s], cur, ca, sl, sh);
         if (cur == EMPTY64) {
@@ -201,7 +202,8 @@ __device__ __forceinline__ void edge_insert(const BuildParams &P, unsigned long 
     h *= 0xD6E8FEB86659FD93ULL;
     unsigned int s = (unsigned int)(h >> 32);
     s = (unsigned int)(((unsigned long long)s * cap) >> 32);
-    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+    const unsigned int max_probe = min(MAX_PROBES, cap);
+    for (unsigned int probe = 0; probe < max_probe; ++probe) {
         unsigned long long cur, cord;
         load_edge_slot(&P.etab[s], cur, cord);
         if (cur == EMPTY64) {
@@ -242,7 +244,8 @@ __device__ __forceinline__ unsigned int node_insert16(const BuildParams &P, cons
     const unsigned int nb = P.ncap >> 1;
     unsigned int b = (unsigned int)(((unsigned long long)(unsigned int)h * nb) >> 32);
     const unsigned int top = (unsigned int)(mine >> FP_SHIFT);
-    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+    const unsigned int max_probe = min(MAX_PROBES, nb);  // a full table is reported after one lap
+    for (unsigned int probe = 0; probe < max_probe; ++probe) {
         NodeSlot16 *B = P.ntab16 + 2 * (size_t)b;
         unsigned long long w0, k0, w1, k1;
         load_bucket(B, w0, k0, w1, k1);
@@ -278,7 +281,8 @@ __device__ __forceinline__ void edge_insert16(const BuildParams &P, unsigned lon
     h ^= h >> 32;
     h *= 0xD6E8FEB86659FD93ULL;
     unsigned int b = (unsigned int)(((h >> 32) * nb) >> 32);
-    for (unsigned int probe = 0; probe < MAX_PROBES; ++probe) {
+    const unsigned int max_probe = min(MAX_PROBES, nb);
+    for (unsigned int probe = 0; probe < max_probe; ++probe) {
         EdgeSlot16 *B = P.etab16 + 2 * (size_t)b;
         unsigned long long c0, o0, c1, o1;
         load_bucket(B, c0, o0, c1, o1);
