@@ -67,3 +67,31 @@ def test_upstream_unit_tests_pass_on_the_drop_in_class(tmp_path):
     n_passed = int(summary.split(" passed")[0].split()[-1])
     assert failed <= OFF_PATH, sorted(failed - OFF_PATH)
     assert n_passed >= 242, summary
+
+
+ALIAS_CONFTEST = '''
+import sys, types
+sys.path.insert(0, %(root)r)
+from amira_b200 import construct_gene, construct_gene_mer, construct_read, construct_node, construct_edge
+pkg = types.ModuleType("amira"); pkg.__path__ = []
+sys.modules["amira"] = pkg
+for name, mod in (("construct_gene", construct_gene), ("construct_gene_mer", construct_gene_mer),
+                  ("construct_read", construct_read), ("construct_node", construct_node),
+                  ("construct_edge", construct_edge)):
+    sys.modules["amira." + name] = mod
+    setattr(pkg, name, mod)
+'''
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REFERENCE, "amira", "construct_graph.py")),
+                    reason="upstream checkout not present")
+def test_upstream_element_tests_pass_on_the_mirror_classes(tmp_path):
+    """upstream's tests of Gene / GeneMer / Read / Node / Edge, with `amira.construct_*` aliased to the mirror
+    modules of this package (the element classes a graph is materialised with when upstream is not bound)"""
+    shutil.copytree(os.path.join(REFERENCE, "tests"), tmp_path / "tests")
+    (tmp_path / "conftest.py").write_text(ALIAS_CONFTEST % {"root": ROOT})
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider"] +
+                         ["tests/" + f for f in FILES[1:]], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    summary = res.stdout.strip().splitlines()[-1]
+    assert res.returncode == 0 and " passed" in summary and "failed" not in summary, res.stdout[-3000:]
+    assert int(summary.split(" passed")[0].split()[-1]) >= 93, summary
