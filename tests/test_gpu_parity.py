@@ -237,3 +237,42 @@ def test_gpu_table_overflow_is_retried():
         g.build(ids, off, 3)
         assert O.diff_arrays(g.arrays(), ref) == [], mask
     g.close()
+
+
+def test_gpu_random_small_inputs(dg):
+    """hundreds of tiny random read sets over tiny vocabularies (tandem repeats, self edges, hairpins,
+    palindromes, multi-edges, empty reads) -- the GPU build and both filters against the C oracle"""
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    from tests.test_random_small_cpu import random_reads
+    n_pal = n_multi = 0
+    for seed in range(300):
+        rng = np.random.default_rng(1000 + seed)
+        reads = random_reads(rng, int(rng.integers(1, 25)), int(rng.integers(2, 9)), int(rng.integers(1, 14)))
+        k = int(rng.integers(1, 6))
+        vocab = O.build_vocabulary(reads)
+        ids, off, _, _ = O.encode_reads(reads, vocab)
+        try:
+            ref = c_oracle.COracleGraph(ids, off, k)
+        except AssertionError:
+            n_pal += 1
+            with pytest.raises(AssertionError):
+                dg.build(ids, off, k)
+            continue
+        dg.build(ids, off, k)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], seed
+        c = int(rng.integers(1, 5))
+        try:
+            ref.remove_low_coverage_components(c)
+        except TypeError:
+            n_multi += 1
+            with pytest.raises(TypeError):
+                dg.remove_low_coverage_components(c)
+            continue
+        dg.remove_low_coverage_components(c)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], seed
+        a, b = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        ref.filter_graph(a, b)
+        dg.filter_graph(a, b)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], seed
+    assert n_pal > 0 and n_multi >= 0
