@@ -280,10 +280,13 @@ int do_build(amira_gmg *h) {
     // unique counts, scaled by the call-count ratio, size the tables at ~50% load; a cold build uses
     // G/4 slots.  Either way an overflow is detected on the device and retried larger.
     int64_t ncap = std::max<int64_t>(4096, G / 4), ecap = std::max<int64_t>(4096, G / 4);
-    // Load factor: a warp waits for the longest probe sequence among its lanes, so the 16-byte tables run
-    // at ~30 % load (measured on the C5 shard: insert kernel 0.91 ms at 50 %, 0.78 ms at 30 %, 0.76 ms at
-    // 25 % -- although the tables then outgrow L2); the 32-byte layouts stay at 50 %.
-    const double nslack = h->n16 ? 3.2 : 2.0, eslack = (G < (1ll << ORD32_P_BITS)) ? 3.2 : 2.0;
+    // Load factor: a warp waits for the longest probe sequence among its lanes, so the 16-byte node table
+    // runs at ~30 % load (measured on the C5 shard: insert kernel 0.91 ms at 50 %, 0.78 ms at 30 %, 0.76 ms
+    // at 25 % -- although the table then outgrows L2).  The edge table is insensitive (0.79 ms at 30 %,
+    // 0.80 ms at 50 %) and stays at 50 %, as do the 32-byte layouts.
+    double nslack = h->n16 ? 3.2 : 2.0, eslack = 2.0;
+    if (const char *e = getenv("AMIRA_NODE_SLACK")) nslack = atof(e);  // developer experiments
+    if (const char *e = getenv("AMIRA_EDGE_SLACK")) eslack = atof(e);
     if (h->hint_nodes > 0) ncap = h->hint_nodes * 2 + 1024;
     else if (h->prev_G > 0 && G <= 4 * h->prev_G)
         ncap = (int64_t)((double)h->prev_nodes * ((double)G / (double)h->prev_G) * nslack) + 4096;
