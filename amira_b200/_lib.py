@@ -15,7 +15,7 @@ PHASES = ("h2d", "windows", "insert", "order", "remap", "incidence", "adjacency"
           "exchange", "emit", "insert_kernel", "emit_nodes")
 
 EXPORTED = (
-    "amira_last_error", "amira_version", "amira_vocab_encode", "amira_gmg_create", "amira_gmg_destroy",
+    "amira_last_error", "amira_version", "amira_vocab_encode", "amira_host_tuple_sha", "amira_host_edge_keys", "amira_gmg_create", "amira_gmg_destroy",
     "amira_gmg_reserve", "amira_gmg_set_profiling", "amira_gmg_phase_ms", "amira_gmg_kernel_launches",
     "amira_gmg_build", "amira_gmg_sync", "amira_gmg_sizes", "amira_gmg_export_nodes", "amira_gmg_export_edges",
     "amira_gmg_export_reads", "amira_gmg_remove_low_coverage_components", "amira_gmg_filter",
@@ -42,6 +42,8 @@ def load():
     lib.amira_version.restype = C.c_char_p
     vp, i64, i32, u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32
     lib.amira_vocab_encode.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp]
+    lib.amira_host_tuple_sha.argtypes = [vp, vp, i64, i32, vp]
+    lib.amira_host_edge_keys.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     lib.amira_gmg_create.argtypes = [C.POINTER(vp), C.c_int, vp]
     lib.amira_gmg_destroy.argtypes = [vp]
     lib.amira_gmg_destroy.restype = None

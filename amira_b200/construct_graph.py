@@ -22,7 +22,7 @@ import weakref
 
 import numpy as np
 
-from . import _lib, encode
+from . import _keys, _lib, encode
 from .construct_edge import Edge, edge_key
 from .construct_gene import Gene, convert_int_strand_to_string, hashlib_hash
 from .construct_gene_mer import GeneMer
@@ -134,7 +134,6 @@ class GeneMerGraph:
         self._read_ids = read_ids
         V = len(vocab)
         # one Gene object per signed id, and its signed SHA integer
-        H = vocab.signed_hashes()
         genes = np.empty(2 * V + 1, object)
         for r, name in enumerate(vocab.names, 1):
             genes[V + r] = C.make_gene(name, 1)
@@ -143,8 +142,7 @@ class GeneMerGraph:
         n_nodes = key.shape[0]
         canon_rows = genes[key + V].tolist() if n_nodes else []
         rc_rows = genes[V - key[:, ::-1]].tolist() if n_nodes else []
-        hash_rows = H[key + V].tolist() if n_nodes else []
-        node_hashes = [hashlib_hash(tuple(row)) for row in hash_rows]
+        node_hashes, node_sha = _keys.node_keys(key, vocab)
         rid_arr = np.empty(len(read_ids), object)
         rid_arr[:] = read_ids
         nr_off = a["node_reads_off"].tolist()
@@ -165,12 +163,9 @@ class GeneMerGraph:
         src, tgt = a["edge_src"].tolist(), a["edge_tgt"].tolist()
         sd, td, ecov = a["edge_sd"].tolist(), a["edge_td"].tolist(), a["edge_cov"].tolist()
         edges = self._edges
-        edge_hashes = []
-        for j in range(len(src)):
-            s, t = node_objs[src[j]], node_objs[tgt[j]]
-            eh = edge_key(node_hashes[src[j]], node_hashes[tgt[j]], sd[j], td[j])
-            edges[eh] = C.make_edge(s, t, sd[j], td[j], ecov[j])
-            edge_hashes.append(eh)
+        edge_hashes = _keys.edge_keys(node_hashes, node_sha, a["edge_src"], a["edge_tgt"], a["edge_sd"], a["edge_td"])
+        for j, eh in enumerate(edge_hashes):
+            edges[eh] = C.make_edge(node_objs[src[j]], node_objs[tgt[j]], sd[j], td[j], ecov[j])
         self._edge_order = edge_hashes
         if edge_hashes:
             eh_arr = np.empty(len(edge_hashes), object)

@@ -38,6 +38,13 @@ class Vocabulary:
             self._blob = (b"".join(enc), off)
         return self._blob
 
+    def sha_bytes(self):
+        """(V, 32) uint8: big-endian SHA-256 integer of every gene name, in rank order"""
+        if getattr(self, "_sha", None) is None:
+            self._sha = np.frombuffer(b"".join(name_hash(n).to_bytes(32, "big") for n in self.names),
+                                      np.uint8).reshape(len(self.names), 32)
+        return self._sha
+
     def signed_hashes(self):
         """object array H with H[id + V] = signed SHA int of gene id (index V unused)"""
         V = len(self.names)

@@ -79,6 +79,16 @@ int amira_vocab_encode(const char *tokens_utf8, const int64_t *tok_off, int64_t 
                        const char *vocab_utf8, const int64_t *vocab_off, int32_t n_vocab,
                        int32_t *out_signed_ids, int64_t *bad_token);
 
+/* Upstream's dictionary keys in bulk, on the host: int(sha256(pickle.dumps(x)).hexdigest(), 16)
+ * (construct_gene.py:5-10) for tuples x of signed 256-bit integers given as 32-byte big-endian
+ * magnitudes + sign flags (pickle protocol 4, the default of CPython 3.8-3.13).  tuple_sha: node keys
+ * (construct_gene_mer.py:94-97) and anything else tuple-shaped; edge_keys: min over both sign choices
+ * (construct_edge.py:104-124) from the node keys and the exported edge arrays.  Outputs are 32-byte
+ * big-endian digests. */
+int amira_host_tuple_sha(const uint8_t *mags, const int8_t *neg, int64_t n_tuples, int32_t arity, uint8_t *out);
+int amira_host_edge_keys(const uint8_t *node_sha, const int32_t *src, const int32_t *tgt, const int8_t *sd,
+                         const int8_t *td, int64_t n_edges, uint8_t *out);
+
 int amira_gmg_create(amira_gmg **h, int device, void *cuda_stream /* NULL: library-owned stream */);
 void amira_gmg_destroy(amira_gmg *h);
 

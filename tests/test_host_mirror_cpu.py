@@ -169,3 +169,28 @@ def test_encoded_reads_reuse_and_binary_round_trip(fake_device, tmp_path, golden
         except AssertionError:
             continue
         assert snapshot(g1) == snapshot(g2)
+
+
+def test_bulk_keys_equal_hashlib_pickle():
+    """csrc/host_keys.cpp restates pickle protocol 4 + SHA-256: every opcode width and sign case, all arities"""
+    import hashlib
+    import pickle
+    import random
+    lib = _lib.load()
+    random.seed(7)
+    vals = [0, 1, -1, 127, 128, 255, 256, -128, -129, -255, -256, 65535, 65536, 2**31 - 1, 2**31, -2**31, -2**31 - 1,
+            2**32, -2**32, 2**63, -2**63, 2**255, -(2**255), 2**256 - 1, -(2**256 - 1), 2**247, -(2**247), 2**248 - 1, -(2**248)]
+    vals += [random.getrandbits(random.choice([8, 16, 31, 32, 33, 64, 200, 255, 256])) * random.choice([1, -1]) for _ in range(500)]
+    for arity in (0, 1, 2, 3, 4, 5, 15):
+        tuples = [tuple(random.choice(vals) for _ in range(arity)) for _ in range(300)]
+        mags = np.zeros((len(tuples), max(arity, 1), 32), np.uint8)
+        neg = np.zeros((len(tuples), max(arity, 1)), np.int8)
+        for i, t in enumerate(tuples):
+            for j, v in enumerate(t):
+                mags[i, j] = np.frombuffer(abs(v).to_bytes(32, "big"), np.uint8)
+                neg[i, j] = v < 0
+        out = np.zeros((len(tuples), 32), np.uint8)
+        assert lib.amira_host_tuple_sha(mags.ctypes.data_as(ctypes.c_void_p), neg.ctypes.data_as(ctypes.c_void_p),
+                                        len(tuples), arity, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        for i, t in enumerate(tuples):
+            assert out[i].tobytes() == hashlib.sha256(pickle.dumps(t, protocol=4)).digest(), (arity, t)
