@@ -12,8 +12,8 @@ from .construct_node import Node
 from .construct_read import Read
 from .device_graph import DeviceGraph
 from .encode import EncodedReads
-from .graph_utils import build_graph, build_multiprocessed_graph
+from .graph_utils import build_graph, build_multiprocessed_graph, get_overall_mean_node_coverages
 
-__all__ = ["GeneMerGraph", "bind_upstream", "build_graph", "build_multiprocessed_graph", "DeviceGraph", "EncodedReads",
+__all__ = ["GeneMerGraph", "bind_upstream", "build_graph", "build_multiprocessed_graph", "DeviceGraph", "EncodedReads", "get_overall_mean_node_coverages",
            "Gene", "GeneMer", "Read", "Node", "Edge", "hashlib_hash"]
 __version__ = "0.1.0"

@@ -124,6 +124,8 @@ class GeneMerGraph:
         arrays = h.arrays()
         h.owner = weakref.ref(self)
         self._materialise(arrays, vocab)
+        # kept for array-level statistics (graph_utils.get_overall_mean_node_coverages)
+        self._incidence_arrays = (arrays["node_reads"], np.diff(off), len(arrays["node_cov"]))
         self._device_synced = True
 
     def _materialise(self, a, vocab):
@@ -400,6 +402,22 @@ class GeneMerGraph:
             return [self._edges[h] for h in s2t], [self._edges[h] for h in t2s]
         return self._edges[s2t], self._edges[t2s]
 
+    def remove_junk_reads(self, error_rate):
+        """upstream construct_graph.py:1398-1420: reads with more than round(n * (1 - error_rate)) filtered
+        (None) nodes are rejected"""
+        reads, positions = self._reads, self._genePositions
+        kept, kept_pos, rejected, rejected_pos = {}, {}, {}, {}
+        for read_id, nodes in self._readNodes.items():
+            ok = nodes.count(None) <= round(len(nodes) * (1 - error_rate))
+            (kept if ok else rejected)[read_id] = reads[read_id]
+            (kept_pos if ok else rejected_pos)[read_id] = positions[read_id]
+        return kept, kept_pos, rejected, rejected_pos
+
+    def get_valid_reads_only(self):
+        """upstream construct_graph.py:1422-1427"""
+        bad = self._readsToCorrect
+        return {r: calls for r, calls in self._reads.items() if r not in bad}
+
     def get_all_node_coverages(self):
         return [n.get_node_coverage() for n in self._nodes.values()]
 
@@ -665,7 +683,8 @@ def bind_upstream(upstream_construct_graph):
 
     ours = GeneMerGraph
     gpu_methods = ("__init__", "_encode", "_build_on_device", "_materialise", "_require_device_state",
-                   "_apply_device_removal", "filter_graph", "remove_low_coverage_components", "_touch")
+                   "_apply_device_removal", "filter_graph", "remove_low_coverage_components", "_touch",
+                   "remove_junk_reads", "get_valid_reads_only")
     ns = {name: ours.__dict__[name] for name in gpu_methods}
     ns["_cls"] = _Up
     ns["_device_ops"] = ()

@@ -194,3 +194,33 @@ def test_bulk_keys_equal_hashlib_pickle():
                                         len(tuples), arity, out.ctypes.data_as(ctypes.c_void_p)) == 0
         for i, t in enumerate(tuples):
             assert out[i].tobytes() == hashlib.sha256(pickle.dumps(t, protocol=4)).digest(), (arity, t)
+
+
+def test_post_build_statistics_match_upstream(fake_device):
+    """graph_utils.get_overall_mean_node_coverages / remove_junk_reads / get_valid_reads_only (the scans callers run
+    right after a build) against upstream's own implementations on upstream's own graph"""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("upstream checkout not present (only in the build container)")
+    cg = ref_harness.load()
+    import amira.graph_utils as up_gu
+    from amira_b200 import synth
+    cfg = synth.CONFIGS["c3"]
+    ids, off = synth.generate(cfg, 0, 400)
+    reads = synth.to_read_dict(ids, off, synth.vocabulary_names(cfg.vocab))
+    positions = {r: [(10 * i, 10 * i + 9) for i in range(len(v))] for r, v in reads.items()}
+    theirs = cg.GeneMerGraph(reads, 3, positions)
+    want = up_gu.get_overall_mean_node_coverages(theirs)
+    for G in (amira_b200.GeneMerGraph, amira_b200.bind_upstream(cg)):
+        g = G(reads, 3, positions)
+        got = amira_b200.get_overall_mean_node_coverages(g)            # from the exported incidence array
+        assert got == want and [type(v) for v in got.values()] == [type(v) for v in want.values()]
+        g._incidence_arrays = None                                      # ... and from the objects
+        assert amira_b200.get_overall_mean_node_coverages(g) == want
+    theirs.filter_graph(3, 1)
+    g = amira_b200.GeneMerGraph(reads, 3, positions)
+    g.filter_graph(3, 1)
+    for rate in (0.8, 0.5, 0.99):
+        assert g.remove_junk_reads(rate) == theirs.remove_junk_reads(rate)
+    assert g.get_valid_reads_only() == theirs.get_valid_reads_only()
+    assert amira_b200.get_overall_mean_node_coverages(g) == up_gu.get_overall_mean_node_coverages(theirs)
