@@ -19,7 +19,7 @@ EXPORTED = (
     "amira_gmg_reserve", "amira_gmg_set_profiling", "amira_gmg_phase_ms", "amira_gmg_kernel_launches",
     "amira_gmg_build", "amira_gmg_sync", "amira_gmg_sizes", "amira_gmg_export_nodes", "amira_gmg_export_edges",
     "amira_gmg_export_reads", "amira_gmg_remove_low_coverage_components", "amira_gmg_filter",
-    "amira_gmg_filter_mask_sizes", "amira_gmg_export_filter_masks", "amira_gmg_nccl_unique_id", "amira_gmg_comm_init", "amira_gmg_atomic_peak", "amira_gmg_debug_layout",
+    "amira_gmg_filter_mask_sizes", "amira_gmg_export_filter_masks", "amira_gmg_nccl_unique_id", "amira_gmg_comm_init", "amira_gmg_atomic_peak", "amira_gmg_debug_layout", "amira_gmg_debug_segsort",
 )
 
 _lib = None
@@ -64,6 +64,7 @@ def load():
     lib.amira_gmg_nccl_unique_id.argtypes = [vp]
     lib.amira_gmg_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.amira_gmg_debug_layout.argtypes = [vp, C.c_int]
+    lib.amira_gmg_debug_segsort.argtypes = [vp, vp, vp, i64, vp, C.POINTER(i64), C.c_int, i64]
     lib.amira_gmg_atomic_peak.argtypes = [vp, i64, i64] + [C.POINTER(C.c_double)] * 3
     _lib = lib
     return lib

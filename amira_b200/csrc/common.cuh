@@ -129,15 +129,19 @@ constexpr int KEY16_BITS = 85;       // 63 in NodeSlot16::key + 22 in the finger
 constexpr int ORD32_P_BITS = 30;
 
 // layout-independent view of the local node table for the passes after the insert
+// info[slot] = {node index once the first-seen order is known, start of the slot's raw node -> reads segment}:
+// one 8-byte gather per window in the scatter pass
 struct NodeView {
     unsigned long long *word;
-    unsigned int *cov, *aux;
+    unsigned int *cov;
+    uint2 *info;
     int wstride;  // in 64-bit words
-    int cstride;  // in 32-bit words (cov and aux)
+    int cstride;  // in 32-bit words
     unsigned int cap;
     __device__ __forceinline__ unsigned long long w(unsigned int s) const { return word[(size_t)s * wstride]; }
     __device__ __forceinline__ unsigned int &c(unsigned int s) const { return cov[(size_t)s * cstride]; }
-    __device__ __forceinline__ unsigned int &a(unsigned int s) const { return aux[(size_t)s * cstride]; }
+    __device__ __forceinline__ unsigned int &a(unsigned int s) const { return info[s].x; }
+    __device__ __forceinline__ unsigned int &base(unsigned int s) const { return info[s].y; }
 };
 
 struct EdgeView {

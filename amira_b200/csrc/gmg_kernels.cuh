@@ -25,9 +25,9 @@
 //                      (construct_graph.py:496-540, 950-958)
 #pragma once
 
-#include <cub/cub.cuh>
-
 #include "common.cuh"
+#include "scan.cuh"
+#include "segsort.cuh"
 
 namespace amira {
 
@@ -43,8 +43,12 @@ constexpr int NR_STAGE = 30;   // reads of a chunk whose offsets are staged in s
 constexpr unsigned int INVALID_VAL = 0xFFFFFFFFu;
 constexpr unsigned int MAX_PROBES = 1u << 15;
 
-enum { ST_ERR = 0, ST_OVERFLOW_N = 1, ST_OVERFLOW_E = 2, ST_UNPACK = 3, ST_COUNT = 4 };
-enum { SZ_W = 0, SZ_NODES = 1, SZ_EDGES = 2, SZ_INC = 3, SZ_SHORT = 4, SZ_FW = 5, SZ_BW = 6, SZ_COUNT = 8 };
+// device-side status words; ST_STALE: the call count assumed by the host (cached from an earlier build of
+// the same device-resident offsets) no longer matches read_off[R]; ST_MAXABS: largest |gene id| staged
+enum { ST_ERR = 0, ST_OVERFLOW_N = 1, ST_OVERFLOW_E = 2, ST_UNPACK = 3, ST_STALE = 4, ST_MAXABS = 5, ST_COUNT = 8 };
+// device-side sizes (the host reads them once, when the caller first asks for a size or an export)
+enum { SZ_W = 0, SZ_NODES = 1, SZ_EDGES = 2, SZ_INC = 3, SZ_SHORT = 4, SZ_FW = 5, SZ_BW = 6, SZ_DUPS = 7,
+       SZ_COMPS = 8, SZ_COUNT = 16 };
 
 struct BuildParams {
     const int32_t *ids;
@@ -65,13 +69,11 @@ struct BuildParams {
     unsigned int ecap;
     int32_t *win_node;
     int8_t *win_dir;
-    int32_t *win_read;
+    uint32_t *win_rank;  // arrival rank of the window among the windows of its node (0-based)
     int32_t *win_start;
     int32_t *win_end;
     int *status;
     int64_t read_base;  // global index of this shard's first read (multi-GPU)
-    int count_cov;      // bump the slot's coverage per window (multi-GPU: the merge needs local counts before the
-                        // sort; on one GPU coverage is the run length of the node in the incidence sort instead)
     int key_bits;       // bits per gene of the packed key (<= 124 bits); 0: gene-mers are compared through ids
     int ids_aligned;    // ids is 16-byte aligned (128-bit staging loads)
 };
@@ -105,6 +107,7 @@ __global__ void k_read_windows(const int64_t *__restrict__ off, int64_t R, int k
         for (int64_t t = (a + INS_TILE - 1) / INS_TILE; t * INS_TILE < b; ++t) tile_r0[t] = (int32_t)r;
     } else if (r == R) {
         nwin[R] = 0;
+        if (R > 0 && off[R] != G) status[ST_STALE] = 1;  // the host's (cached) call count is out of date
     }
     unsigned m = __ballot_sync(0xffffffffu, shortr);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long *)&sizes[SZ_SHORT], (unsigned long long)__popc(m));
@@ -341,28 +344,34 @@ __global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(
         // ---- stage the chunk (+ halo); c0 is a multiple of 128 calls
         {
             const int32_t *src = P.ids + c0;
-            // an id must leave the all-ones field value free: an all-ones key half means "not published"
-            const unsigned int bias = packed ? (1u << (kb - 1)) : 0u, lim = packed ? ((1u << kb) - 1u) : 0xFFFFFFFFu;
-            bool bad = false;
+            // a packed field holds g + 2^(kb-1); the canonical form also packs -g, and the all-ones and all-zero
+            // field values stay free (an all-ones key half means "not published"): |g| <= 2^(kb-1) - 2
+            const unsigned int lim = packed ? ((1u << (kb - 1)) - 2u) : 0x7FFFFFFFu;
+            unsigned int mx = 0;
             const int i4 = lane * 4;
             if (P.ids_aligned && i4 + 4 <= n_load) {
                 const int4 v = __ldcs(reinterpret_cast<const int4 *>(src) + lane);  // streamed once: evict first
                 *reinterpret_cast<int4 *>(&S.ids[i4]) = v;
-                bad = ((unsigned int)v.x + bias >= lim) | ((unsigned int)v.y + bias >= lim) |
-                      ((unsigned int)v.z + bias >= lim) | ((unsigned int)v.w + bias >= lim);
+                mx = max(max((unsigned int)abs(v.x), (unsigned int)abs(v.y)), max((unsigned int)abs(v.z), (unsigned int)abs(v.w)));
             } else {
                 for (int i = i4; i < i4 + 4 && i < n_load; ++i) {
                     const int g = __ldcs(src + i);
                     S.ids[i] = g;
-                    bad |= ((unsigned int)g + bias >= lim);
+                    mx = max(mx, (unsigned int)abs(g));
                 }
             }
             for (int i = WC + lane; i < n_load; i += 32) {
                 const int g = __ldcs(src + i);
                 S.ids[i] = g;
-                bad |= ((unsigned int)g + bias >= lim);
+                mx = max(mx, (unsigned int)abs(g));
             }
-            if (packed && bad) P.status[ST_UNPACK] = 1;  // the host redoes the build unpacked
+            // abs(INT_MIN) stays 0x80000000 as unsigned: larger than any limit, as it must be
+            if (__any_sync(0xffffffffu, mx > lim) && packed) {
+                if (mx > lim) P.status[ST_UNPACK] = 1;  // the host redoes the build with wider fields
+            }
+            // largest |id| of this input, for the key width of the next build on the handle
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0 && mx > ((volatile unsigned int *)P.status)[ST_MAXABS]) atomicMax((unsigned int *)&P.status[ST_MAXABS], mx);
         }
         *reinterpret_cast<int4 *>(&S.j[lane * 4]) = make_int4(0, 0, 0, 0);
         for (int i = lane; i <= nr && i <= NR_STAGE + 1; i += 32) S.off[i] = P.off[r_lo + i];
@@ -463,13 +472,15 @@ __global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(
                     }
                     val = slot | ((unsigned int)dirneg << 31);
                     if (!halo) {
-                        if (P.count_cov) atomicAdd(N16 ? &P.ncov[slot] : &P.ntab[slot].cov, 1u);
+                        // Node.nodeCoverage: one per window (counts from 0xFFFFFFFF); the value before the increment
+                        // is this window's place in the node's raw read list
+                        const unsigned int before = atomicAdd(N16 ? &P.ncov[slot] : &P.ntab[slot].cov, 1u);
                         const long long rs = (j <= NR_STAGE + 1) ? S.off[j] : P.off[r_lo + j];
                         const long long wo = (j <= NR_STAGE) ? S.woff[j] : P.win_off[r_lo + j];
                         const int64_t w = wo + (p - rs);
                         __stcs(&P.win_node[w], (int32_t)slot);  // streaming stores: keep the tables in L2
                         __stcs(&P.win_dir[w], (signed char)dir);
-                        __stcs(&P.win_read[w], (int32_t)(r_lo + j));
+                        __stcs(&P.win_rank[w], before + 1u);
                         if (P.ps) {
                             P.win_start[w] = __ldg(P.ps + p);
                             P.win_end[w] = __ldg(P.pe + p + k - 1);
@@ -519,373 +530,6 @@ __global__ void k_boundary_edges(const BuildParams P) {
     const unsigned long long ord = ((unsigned long long)p0 << 2) | ((unsigned long long)(sa > sb) << 1) | sdneg;
     if (E16) edge_insert16(P, key, (unsigned int)ord);
     else edge_insert(P, key, ord);
-}
-
-// ---------------------------------------------------------------------------------------------
-// first-seen order: bit p of bm_node is set iff a node was first seen at call p; bm_ea likewise for
-// undirected edge entries (first pair at p), bm_eb additionally when the entry is not a self-edge
-// (it then expands to two directed edges).
-__global__ void k_mark_first(const NodeView nv, const EdgeView ev, unsigned int *__restrict__ bm_node,
-                             unsigned int *__restrict__ bm_ea, unsigned int *__restrict__ bm_eb) {
-    const unsigned int stride = gridDim.x * blockDim.x;
-    const unsigned int ncap = nv.cap, ecap = ev.cap;
-    const unsigned int n = max(ncap, ecap);
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
-        if (s < ncap) {
-            unsigned long long w = nv.w(s);
-            if (w != EMPTY64) {
-                unsigned long long p = (w >> 1) & P_MASK;
-                atomicOr(&bm_node[p >> 5], 1u << (p & 31));
-            }
-        }
-        if (s < ecap) {
-            unsigned long long key, eord;
-            unsigned int ecov;
-            if (ev.get(s, key, eord, ecov)) {
-                unsigned long long p = eord >> 2;
-                atomicOr(&bm_ea[p >> 5], 1u << (p & 31));
-                unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
-                if (lo != hi) atomicOr(&bm_eb[p >> 5], 1u << (p & 31));
-            }
-        }
-    }
-}
-
-__global__ void k_popcount(const unsigned int *__restrict__ bm_node, const unsigned int *__restrict__ bm_ea,
-                           const unsigned int *__restrict__ bm_eb, int64_t n_words, int *__restrict__ cnt_node,
-                           int *__restrict__ cnt_edge) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_words) {
-        cnt_node[i] = __popc(bm_node[i]);
-        cnt_edge[i] = __popc(bm_ea[i]) + __popc(bm_eb[i]);
-    } else if (i == n_words) {
-        cnt_node[i] = 0;
-        cnt_edge[i] = 0;
-    }
-}
-
-__global__ void k_collect_sizes(const int64_t *__restrict__ win_off, int64_t R, const int *__restrict__ pref_node,
-                                const int *__restrict__ pref_edge, int64_t n_words, long long *__restrict__ sizes) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        sizes[SZ_W] = win_off[R];
-        sizes[SZ_NODES] = pref_node[n_words];
-        sizes[SZ_EDGES] = pref_edge[n_words];
-    }
-}
-
-__global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids, int k,
-                             const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
-                             int32_t *__restrict__ node_key, uint32_t *__restrict__ node_cov,
-                             int8_t *__restrict__ node_dir, int32_t *__restrict__ parent) {
-    const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
-        unsigned long long w = nv.w(s);
-        if (w == EMPTY64) continue;
-        const unsigned long long p = (w >> 1) & P_MASK;
-        const int neg = (int)(w & 1ull);
-        const int idx = pref_node[p >> 5] + __popc(bm_node[p >> 5] & ((1u << (p & 31)) - 1u));
-        nv.a(s) = (unsigned int)idx;
-        if (node_cov) node_cov[idx] = nv.c(s) + 1u;
-        node_dir[idx] = neg ? -1 : 1;
-        parent[idx] = idx;
-        for (int j = 0; j < k; ++j)
-            node_key[(int64_t)idx * k + j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
-    }
-}
-
-__device__ __forceinline__ int uf_find(int32_t *parent, int x) {
-    // path halving; races only ever replace a parent by one of its ancestors
-    while (true) {
-        int p = ((volatile int32_t *)parent)[x];
-        if (p == x) return x;
-        int gp = ((volatile int32_t *)parent)[p];
-        if (gp != p) parent[x] = gp;
-        x = p;
-    }
-}
-
-// Roots are linked by a hashed priority, not by index: first-seen node indices follow the reads, so
-// linking by index would build list-shaped trees (node i+1 under node i) and serialise every find.
-// Random linking keeps the expected depth logarithmic; the component's first node is recovered
-// afterwards with an atomicMin per root (k_cc_flatten).
-__device__ __forceinline__ unsigned int uf_prio(int x) {
-    unsigned int v = (unsigned int)x * 0x9E3779B1u;
-    v ^= v >> 15;
-    v *= 0x85EBCA77u;
-    v ^= v >> 13;
-    return v;
-}
-
-__device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
-    int ra = uf_find(parent, a), rb = uf_find(parent, b);
-    while (ra != rb) {
-        const unsigned int pa = uf_prio(ra), pb = uf_prio(rb);
-        if (pa < pb || (pa == pb && ra < rb)) {
-            int t = ra;
-            ra = rb;
-            rb = t;
-        }
-        // hook the root of higher priority value under the other one
-        int old = atomicCAS(&parent[ra], ra, rb);
-        if (old == ra) return;
-        ra = uf_find(parent, old);
-        rb = uf_find(parent, rb);
-    }
-}
-
-__global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
-                             const unsigned int *__restrict__ bm_ea, const unsigned int *__restrict__ bm_eb,
-                             const int *__restrict__ pref_edge, int32_t *__restrict__ e_src,
-                             int32_t *__restrict__ e_tgt, int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td,
-                             uint32_t *__restrict__ e_cov, int32_t *__restrict__ parent) {
-    const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ev.cap; s += stride) {
-        unsigned long long key, ord;
-        unsigned int ecov;
-        if (!ev.get(s, key, ord, ecov)) continue;
-        const unsigned long long p = ord >> 2;
-        const unsigned int below = (1u << (p & 31)) - 1u;
-        const int idx = pref_edge[p >> 5] + __popc(bm_ea[p >> 5] & below) + __popc(bm_eb[p >> 5] & below);
-        const unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
-        const int rel = (key & 1ull) ? 1 : -1;
-        const bool src_hi = (ord >> 1) & 1ull;
-        const int src = (int)nv.a(src_hi ? hi : lo), tgt = (int)nv.a(src_hi ? lo : hi);
-        const int sd = (ord & 1ull) ? -1 : 1, td = rel * sd;
-        const uint32_t cov = ecov + 1u;
-        if (lo != hi) {
-            // forward edge S->T, then the reverse edge T->S with directions (-td, -sd)
-            e_src[idx] = src; e_tgt[idx] = tgt; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = cov;
-            e_src[idx + 1] = tgt; e_tgt[idx + 1] = src; e_sd[idx + 1] = (int8_t)-td; e_td[idx + 1] = (int8_t)-sd;
-            e_cov[idx + 1] = cov;
-            if (parent) uf_union(parent, src, tgt);
-        } else {
-            // S == T: forward and reverse are the same Edge object, incremented twice per pair
-            e_src[idx] = src; e_tgt[idx] = src; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = 2u * cov;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-__global__ void k_remap_windows(const NodeView nv, int32_t *__restrict__ win_node, int64_t W) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += stride)
-        win_node[w] = (int32_t)nv.a((unsigned int)win_node[w]);
-}
-
-// after the stable sort by node: duplicates (same node, same read) are adjacent.  Count them per
-// node (rare), flag the survivors, and record where each node's run starts: the run length is the
-// node's coverage (construct_graph.py:71,86,100 counts one per window).
-__global__ void k_incidence_flags(const int32_t *__restrict__ keys, const int32_t *__restrict__ vals, int64_t W,
-                                  uint8_t *__restrict__ flags, uint32_t *__restrict__ dups,
-                                  uint32_t *__restrict__ run_start) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < W; i += stride) {
-        const int32_t key = keys[i];
-        const bool new_node = (i == 0) || key != keys[i - 1];
-        const bool first = new_node || vals[i] != vals[i - 1];
-        flags[i] = first;
-        if (!first) atomicAdd(&dups[key], 1u);
-        if (new_node) run_start[key] = (uint32_t)i;
-    }
-}
-
-// per-node number of unique reads; cov_from_runs: also the coverage, from the run lengths
-__global__ void k_incidence_counts(uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ run_start,
-                                   const uint32_t *__restrict__ dups, int64_t n_nodes, int64_t W, int cov_from_runs,
-                                   int64_t *__restrict__ reads_off) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) {
-        uint32_t cov;
-        if (cov_from_runs) {
-            cov = (i + 1 < n_nodes ? run_start[i + 1] : (uint32_t)W) - run_start[i];
-            node_cov[i] = cov;
-        } else {
-            cov = node_cov[i];
-        }
-        reads_off[i] = (int64_t)cov - (int64_t)dups[i];
-    } else if (i == n_nodes) {
-        reads_off[i] = 0;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// adjacency: forward list of node n = edges with source n and stored source direction +1, in edge
-// creation order (construct_graph.py:287-298); backward list likewise with -1.
-__global__ void k_adj_keys(const int32_t *__restrict__ e_src, const int8_t *__restrict__ e_sd, int64_t n_edges,
-                           int64_t n_nodes, uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
-                           int64_t *__restrict__ deg) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_edges) return;
-    uint32_t key = (uint32_t)e_src[e] + (e_sd[e] < 0 ? (uint32_t)n_nodes : 0u);
-    keys[e] = key;
-    vals[e] = (int32_t)e;
-    atomicAdd((unsigned long long *)&deg[key], 1ull);
-}
-
-// ---------------------------------------------------------------------------------------------
-// union-find over the emitted edges in first-seen order (each undirected adjacency once)
-__global__ void k_union_edges(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt, int64_t n_edges,
-                              int32_t *__restrict__ parent) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_edges) return;
-    const int s = e_src[e], t = e_tgt[e];
-    if (s < t) uf_union(parent, s, t);
-}
-
-// root of every node (read-only walk: the unions are over, trees are shallow thanks to the random
-// linking) and each component's first node (cmin starts at 0xFFFFFFFF)
-__global__ void k_cc_flatten(const int32_t *__restrict__ parent, int64_t n_nodes, unsigned int *__restrict__ cmin,
-                             uint32_t *__restrict__ root) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    int r = (int)i;
-    for (int p = parent[r]; p != r; p = parent[r]) r = p;
-    root[i] = (uint32_t)r;
-    // threads run roughly in index order: after the first few updates the minimum is final and the
-    // remaining nodes of a (giant) component skip the atomic
-    if ((unsigned int)i < ((volatile unsigned int *)cmin)[r]) atomicMin(&cmin[r], (unsigned int)i);
-}
-
-__global__ void k_cc_first(const uint32_t *__restrict__ root, const unsigned int *__restrict__ cmin, int64_t n_nodes,
-                           int *__restrict__ is_first) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) is_first[i] = (cmin[root[i]] == (unsigned int)i);
-    else if (i == n_nodes) is_first[i] = 0;
-}
-
-// component ids 1, 2, ... in order of each component's first node (construct_graph.py:920-927);
-// comp holds the roots on entry
-__global__ void k_cc_number(const unsigned int *__restrict__ cmin, const int *__restrict__ first_rank, int64_t n_nodes,
-                            uint32_t *__restrict__ comp) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) comp[i] = (uint32_t)first_rank[cmin[comp[i]]] + 1u;
-}
-
-// ---------------------------------------------------------------------------------------------
-// filters
-__global__ void k_component_max(const uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ comp,
-                                int64_t n_nodes, uint32_t *__restrict__ comp_max) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) {
-        // one giant component is the common case: read first, the maximum only ever grows
-        const uint32_t c = comp[i], v = node_cov[i];
-        if (v > ((volatile uint32_t *)comp_max)[c]) atomicMax(&comp_max[c], v);
-    }
-}
-
-// keep flags: mode 0 = coverage >= thr (filter_graph), mode 1 = component max >= thr
-__global__ void k_node_keep(const uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ comp,
-                            const uint32_t *__restrict__ comp_max, int64_t n_nodes, uint32_t thr, int mode,
-                            int *__restrict__ keep) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) keep[i] = mode == 0 ? (node_cov[i] >= thr) : (comp_max[comp[i]] >= thr);
-    else if (i == n_nodes) keep[i] = 0;
-}
-
-__global__ void k_edge_keep(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt,
-                            const uint32_t *__restrict__ e_cov, const int *__restrict__ node_keep, int64_t n_edges,
-                            uint32_t thr, int *__restrict__ keep) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n_edges) keep[e] = (e_cov[e] >= thr) && node_keep[e_src[e]] && node_keep[e_tgt[e]];
-    else if (e == n_edges) keep[e] = 0;
-}
-
-// upstream's remove_node dies with TypeError when a doomed node has two edges to one neighbour
-// (get_edge_hashes_between_nodes returns lists, construct_graph.py:383-386, 479-482)
-__global__ void k_multi_edge_check(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt,
-                                   const int32_t *__restrict__ adj_edges, const int64_t *__restrict__ adj_off,
-                                   const int *__restrict__ node_keep, int64_t n_nodes, int *__restrict__ status) {
-    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_nodes || node_keep[n]) return;
-    // the node's forward edges live at [adj_off[n], adj_off[n+1]), its backward ones at [adj_off[N+n], ...)
-    for (int pass = 0; pass < 2; ++pass) {
-        int64_t a0 = adj_off[n + pass * n_nodes], a1 = adj_off[n + pass * n_nodes + 1];
-        for (int64_t i = a0; i < a1; ++i) {
-            int32_t t = e_tgt[adj_edges[i]];
-            for (int pass2 = pass; pass2 < 2; ++pass2) {
-                int64_t b0 = pass2 == pass ? i + 1 : adj_off[n + n_nodes], b1 = adj_off[n + pass2 * n_nodes + 1];
-                for (int64_t j = b0; j < b1; ++j)
-                    if (e_tgt[adj_edges[j]] == t) status[ST_ERR] = AMIRA_E_MULTI_EDGE;
-            }
-        }
-    }
-}
-
-__global__ void k_compact_nodes(const int *__restrict__ keep, const int *__restrict__ newidx, int64_t n_nodes, int k,
-                                const int32_t *__restrict__ key_in, const uint32_t *__restrict__ cov_in,
-                                const int8_t *__restrict__ dir_in, const uint32_t *__restrict__ comp_in,
-                                const int64_t *__restrict__ roff_in, int32_t *__restrict__ key_out,
-                                uint32_t *__restrict__ cov_out, int8_t *__restrict__ dir_out,
-                                uint32_t *__restrict__ comp_out, int64_t *__restrict__ rcount_out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) rcount_out[newidx[n_nodes]] = 0;
-    if (i >= n_nodes || !keep[i]) return;
-    const int o = newidx[i];
-    for (int j = 0; j < k; ++j) key_out[(int64_t)o * k + j] = key_in[i * k + j];
-    cov_out[o] = cov_in[i];
-    dir_out[o] = dir_in[i];
-    comp_out[o] = comp_in[i];
-    rcount_out[o] = roff_in[i + 1] - roff_in[i];
-}
-
-// one warp per surviving node copies its read list
-__global__ void k_compact_incidence(const int *__restrict__ keep, const int *__restrict__ newidx, int64_t n_nodes,
-                                    const int64_t *__restrict__ roff_in, const int32_t *__restrict__ reads_in,
-                                    const int64_t *__restrict__ roff_out, int32_t *__restrict__ reads_out) {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_nodes || !keep[warp]) return;
-    const int64_t a = roff_in[warp], n = roff_in[warp + 1] - a, b = roff_out[newidx[warp]];
-    for (int64_t i = lane; i < n; i += 32) reads_out[b + i] = reads_in[a + i];
-}
-
-__global__ void k_compact_edges(const int *__restrict__ keep, const int *__restrict__ newidx,
-                                const int *__restrict__ node_newidx, int64_t n_edges,
-                                const int32_t *__restrict__ src_in, const int32_t *__restrict__ tgt_in,
-                                const int8_t *__restrict__ sd_in, const int8_t *__restrict__ td_in,
-                                const uint32_t *__restrict__ cov_in, int32_t *__restrict__ src_out,
-                                int32_t *__restrict__ tgt_out, int8_t *__restrict__ sd_out,
-                                int8_t *__restrict__ td_out, uint32_t *__restrict__ cov_out) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_edges || !keep[e]) return;
-    const int o = newidx[e];
-    src_out[o] = node_newidx[src_in[e]];
-    tgt_out[o] = node_newidx[tgt_in[e]];
-    sd_out[o] = sd_in[e];
-    td_out[o] = td_in[e];
-    cov_out[o] = cov_in[e];
-}
-
-// remove_node_from_reads (construct_graph.py:442-461): windows of removed nodes become None and
-// their reads join _readsToCorrect
-__global__ void k_mask_windows(const int *__restrict__ node_keep, const int *__restrict__ node_newidx,
-                               int32_t *__restrict__ win_node, int8_t *__restrict__ win_dir,
-                               const int32_t *__restrict__ win_read, int32_t *__restrict__ win_start,
-                               int32_t *__restrict__ win_end, int64_t W, uint8_t *__restrict__ to_correct) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += stride) {
-        const int n = win_node[w];
-        if (n < 0) continue;
-        if (node_keep[n]) {
-            win_node[w] = node_newidx[n];
-        } else {
-            win_node[w] = -1;
-            win_dir[w] = 0;
-            if (win_start) {
-                win_start[w] = -1;
-                win_end[w] = -1;
-            }
-            to_correct[win_read[w]] = 1;
-        }
-    }
-}
-
-__global__ void k_filter_sizes(const int *__restrict__ node_newidx, int64_t n_nodes, const int *__restrict__ edge_newidx,
-                               int64_t n_edges, long long *__restrict__ sizes) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        sizes[SZ_NODES] = node_newidx[n_nodes];
-        sizes[SZ_EDGES] = edge_newidx[n_edges];
-    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,618 @@
+// post_kernels.cuh -- everything after the insert kernel: first-seen order, node / edge arrays,
+// per-read lists, node -> reads and node -> edges transposes, components, filters.
+//
+// No kernel here takes an element count from the host that the host would first have to read back
+// from the device: node, edge and window counts live in the device-side `sizes` array (Cnt::p), so a
+// whole build is enqueued without a single host synchronisation (and can be captured in a CUDA
+// graph).  Launch grids are sized from host-known upper bounds (call count, table capacities) and the
+// kernels grid-stride up to the device-side count.
+#pragma once
+
+#include "gmg_kernels.cuh"
+
+namespace amira {
+
+// an element count that lives on the device (p != nullptr) or is known to the host (v)
+struct Cnt {
+    const long long *p;
+    long long v;
+    __device__ __forceinline__ long long get() const { return p ? *p : v; }
+};
+
+constexpr int WT = 128;  // windows per tile of the window -> read map
+
+__global__ void k_fill_u32(uint32_t *__restrict__ a, const Cnt n, const long long mul, const long long add, const uint32_t v) {
+    const long long m = n.get() * mul + add;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) a[i] = v;
+}
+
+__global__ void k_fill_u64(unsigned long long *__restrict__ a, const Cnt n, const long long mul, const long long add,
+                           const unsigned long long v) {
+    const long long m = n.get() * mul + add;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) a[i] = v;
+}
+
+// ---- per-read window offsets (scan functors) ---------------------------------------------------
+// win_off = exclusive scan of the per-read window counts (in place); every read also records itself as
+// the owner of each 128-window tile whose first window it holds (the window -> read map of the passes
+// that walk the windows: nothing stores a read index per window)
+struct WinOffLoad {
+    const int64_t *nwin;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return (unsigned long long)nwin[i]; }
+};
+struct WinOffStore {
+    int64_t *win_off;
+    int32_t *wtile_r0;
+    long long R;
+    long long *sizes;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long val) const {
+        win_off[i] = (int64_t)excl;
+        const long long a = (long long)excl, b = a + (long long)val;
+        for (long long t = (a + WT - 1) / WT; t * WT < b; ++t) wtile_r0[t] = (int32_t)i;
+        if (i == R) sizes[SZ_W] = a;
+    }
+};
+
+// Which read each of the 128 windows of tile `tile` belongs to, relative to the tile's first read
+// (returned): sj[0..128) per warp.  Reads without windows own nothing and are skipped by construction.
+__device__ __forceinline__ int tile_reads(const int64_t *__restrict__ win_off, const int32_t *__restrict__ wtile_r0,
+                                          const long long tile, const long long n_wtiles, const long long R,
+                                          int *sj, const int lane) {
+    const long long w0 = tile * WT;
+    const int r_lo = wtile_r0[tile];
+    const int r_hi = (tile + 1 < n_wtiles) ? wtile_r0[tile + 1] : (int)(R - 1);
+    *reinterpret_cast<int4 *>(&sj[lane * 4]) = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    for (int j = 1 + lane; j <= r_hi - r_lo; j += 32) {
+        const long long o = win_off[r_lo + j] - w0;
+        if (o < WT) atomicMax(&sj[(int)o], j);
+    }
+    __syncwarp();
+    int4 v = *reinterpret_cast<int4 *>(&sj[lane * 4]);
+    v.y = max(v.x, v.y);
+    v.z = max(v.y, v.z);
+    v.w = max(v.z, v.w);
+    int incl = v.w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl = max(incl, o);
+    }
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0;
+    v.x = max(v.x, excl);
+    v.y = max(v.y, excl);
+    v.z = max(v.z, excl);
+    v.w = max(v.w, excl);
+    *reinterpret_cast<int4 *>(&sj[lane * 4]) = v;
+    __syncwarp();
+    return r_lo;
+}
+
+// ---- first-seen order ---------------------------------------------------------------------------
+// bit p of bm_node is set iff a node was first seen at call p; bm_ea likewise for undirected edge
+// entries (first pair at p), bm_eb additionally when the entry is not a self-edge (it then expands to
+// two directed edges).  The rank of a node / edge in upstream's dict order is the number of set bits
+// below its own: a prefix popcount, no sort.
+__global__ void k_mark_first(const NodeView nv, const EdgeView ev, unsigned int *__restrict__ bm_node,
+                             unsigned int *__restrict__ bm_ea, unsigned int *__restrict__ bm_eb) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int ncap = nv.cap, ecap = ev.cap;
+    const unsigned int n = max(ncap, ecap);
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+        if (s < ncap) {
+            unsigned long long w = nv.w(s);
+            if (w != EMPTY64) {
+                unsigned long long p = (w >> 1) & P_MASK;
+                atomicOr(&bm_node[p >> 5], 1u << (p & 31));
+            }
+        }
+        if (s < ecap) {
+            unsigned long long key, eord;
+            unsigned int ecov;
+            if (ev.get(s, key, eord, ecov)) {
+                unsigned long long p = eord >> 2;
+                atomicOr(&bm_ea[p >> 5], 1u << (p & 31));
+                unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
+                if (lo != hi) atomicOr(&bm_eb[p >> 5], 1u << (p & 31));
+            }
+        }
+    }
+}
+
+// one scan for both ranks: node count in the upper 31 bits of the scanned value, directed-edge count below
+struct RankLoad {
+    const unsigned int *bm_node, *bm_ea, *bm_eb;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const {
+        return ((unsigned long long)__popc(bm_node[i]) << 31) | (unsigned long long)(__popc(bm_ea[i]) + __popc(bm_eb[i]));
+    }
+};
+// A build the insert kernel gave up on (palindromic gene-mer, full table, stale call count) is POISONED:
+// its tables are not a graph.  Nothing waits for the host to notice, so the counts the later passes run on
+// are zeroed here and they all become no-ops; the host sees the status words and raises or retries.
+__device__ __forceinline__ bool poisoned(const int *status) {
+    return (status[ST_ERR] | status[ST_OVERFLOW_N] | status[ST_OVERFLOW_E] | status[ST_UNPACK] | status[ST_STALE]) != 0;
+}
+struct RankStore {
+    int *pref_node, *pref_edge;
+    long long n_words;
+    long long *sizes;
+    const int *status;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        const int nn = (int)(excl >> 31), ne = (int)(excl & 0x7FFFFFFFull);
+        pref_node[i] = nn;
+        pref_edge[i] = ne;
+        if (i == n_words) {
+            const bool bad = poisoned(status);
+            sizes[SZ_NODES] = bad ? 0 : nn;
+            sizes[SZ_EDGES] = bad ? 0 : ne;
+            if (bad) sizes[SZ_W] = 0;
+        }
+    }
+};
+
+// start of every slot's raw node -> reads segment: exclusive scan of the window counts in TABLE order (known as
+// soon as the insert kernel is done; the first-seen order is not needed to place the reads)
+struct SlotBaseLoad {
+    NodeView nv;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return nv.c((unsigned int)i) + 1u; }
+};
+struct SlotBaseStore {
+    NodeView nv;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        if (i < (long long)nv.cap) nv.base((unsigned int)i) = (unsigned int)excl;
+    }
+};
+
+// node arrays in first-seen order; node_cov[idx] = windows counted by the insert kernel
+__global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids, int k,
+                             const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
+                             int32_t *__restrict__ node_key, uint32_t *__restrict__ node_cov,
+                             int8_t *__restrict__ node_dir, int32_t *__restrict__ parent,
+                             uint32_t *__restrict__ node_src) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
+        unsigned long long w = nv.w(s);
+        if (w == EMPTY64) continue;
+        const unsigned long long p = (w >> 1) & P_MASK;
+        const int neg = (int)(w & 1ull);
+        const int idx = pref_node[p >> 5] + __popc(bm_node[p >> 5] & ((1u << (p & 31)) - 1u));
+        nv.a(s) = (unsigned int)idx;
+        node_cov[idx] = nv.c(s) + 1u;
+        node_src[idx] = nv.base(s);
+        node_dir[idx] = neg ? -1 : 1;
+        parent[idx] = idx;
+        for (int j = 0; j < k; ++j)
+            node_key[(int64_t)idx * k + j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
+    }
+}
+
+// ---- union-find -----------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int32_t *parent, int x) {
+    // path halving; races only ever replace a parent by one of its ancestors
+    while (true) {
+        int p = ((volatile int32_t *)parent)[x];
+        if (p == x) return x;
+        int gp = ((volatile int32_t *)parent)[p];
+        if (gp != p) parent[x] = gp;
+        x = p;
+    }
+}
+
+// Roots are linked by a hashed priority, not by index: first-seen node indices follow the reads, so
+// linking by index would build list-shaped trees (node i+1 under node i) and serialise every find.
+// Random linking keeps the expected depth logarithmic; the component's first node is recovered
+// afterwards with an atomicMin per root (k_cc_flatten).
+__device__ __forceinline__ unsigned int uf_prio(int x) {
+    unsigned int v = (unsigned int)x * 0x9E3779B1u;
+    v ^= v >> 15;
+    v *= 0x85EBCA77u;
+    v ^= v >> 13;
+    return v;
+}
+
+__device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
+    int ra = uf_find(parent, a), rb = uf_find(parent, b);
+    while (ra != rb) {
+        const unsigned int pa = uf_prio(ra), pb = uf_prio(rb);
+        if (pa < pb || (pa == pb && ra < rb)) {
+            int t = ra;
+            ra = rb;
+            rb = t;
+        }
+        // hook the root of higher priority value under the other one
+        int old = atomicCAS(&parent[ra], ra, rb);
+        if (old == ra) return;
+        ra = uf_find(parent, old);
+        rb = uf_find(parent, rb);
+    }
+}
+
+// edge arrays in first-seen order: each undirected table entry expands to upstream's forward edge
+// S->T and reverse edge T->S (-td, -sd), or to one self edge counted twice (construct_graph.py:246-277);
+// the adjacency degree of the source side of every directed edge is counted on the way
+__global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
+                             const unsigned int *__restrict__ bm_ea, const unsigned int *__restrict__ bm_eb,
+                             const int *__restrict__ pref_edge, const Cnt n_nodes, int32_t *__restrict__ e_src,
+                             int32_t *__restrict__ e_tgt, int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td,
+                             uint32_t *__restrict__ e_cov, unsigned long long *__restrict__ deg,
+                             const int *__restrict__ status) {
+    if (poisoned(status)) return;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const long long N = n_nodes.get();
+    for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ev.cap; s += stride) {
+        unsigned long long key, ord;
+        unsigned int ecov;
+        if (!ev.get(s, key, ord, ecov)) continue;
+        const unsigned long long p = ord >> 2;
+        const unsigned int below = (1u << (p & 31)) - 1u;
+        const int idx = pref_edge[p >> 5] + __popc(bm_ea[p >> 5] & below) + __popc(bm_eb[p >> 5] & below);
+        const unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
+        const int rel = (key & 1ull) ? 1 : -1;
+        const bool src_hi = (ord >> 1) & 1ull;
+        const int src = (int)nv.a(src_hi ? hi : lo), tgt = (int)nv.a(src_hi ? lo : hi);
+        const int sd = (ord & 1ull) ? -1 : 1, td = rel * sd;
+        const uint32_t cov = ecov + 1u;
+        if (lo != hi) {
+            // forward edge S->T, then the reverse edge T->S with directions (-td, -sd)
+            e_src[idx] = src; e_tgt[idx] = tgt; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = cov;
+            e_src[idx + 1] = tgt; e_tgt[idx + 1] = src; e_sd[idx + 1] = (int8_t)-td; e_td[idx + 1] = (int8_t)-sd;
+            e_cov[idx + 1] = cov;
+            atomicAdd(&deg[src + (sd < 0 ? N : 0)], 1ull);
+            atomicAdd(&deg[tgt + (-td < 0 ? N : 0)], 1ull);
+        } else {
+            // S == T: forward and reverse are the same Edge object, incremented twice per pair
+            e_src[idx] = src; e_tgt[idx] = src; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = 2u * cov;
+            atomicAdd(&deg[src + (sd < 0 ? N : 0)], 1ull);
+        }
+    }
+}
+
+// ---- per-read node lists + node -> reads scatter ------------------------------------------------------
+// One warp per 128-window tile: slot -> node index for the per-read lists (construct_graph.py:165-178)
+// and, on the same pass, the window's read is appended to its node's segment through an atomic cursor
+// (arrival order; k_segsort_main sorts the segments afterwards).
+struct CovLoad {
+    const uint32_t *cov;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return cov[i]; }
+};
+struct CovStore {
+    int64_t *reads_off;
+    Cnt n;
+    long long *sizes;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        reads_off[i] = (int64_t)excl;
+        if (i == n.get()) sizes[SZ_INC] = (long long)excl;
+    }
+};
+
+__global__ void __launch_bounds__(256) k_scatter_windows(const NodeView nv, int32_t *__restrict__ win_node,
+                                                         const uint32_t *__restrict__ win_rank,
+                                                         const int64_t *__restrict__ win_off,
+                                                         const int32_t *__restrict__ wtile_r0,
+                                                         const long long *__restrict__ sizes, const long long R,
+                                                         uint32_t *__restrict__ raw, const int32_t read_base) {
+    __shared__ __align__(16) int s_j[8][WT];
+    const int lane = threadIdx.x & 31;
+    int *sj = s_j[threadIdx.x >> 5];
+    const long long W = sizes[SZ_W];
+    const long long n_wtiles = (W + WT - 1) / WT;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long tile = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; tile < n_wtiles; tile += n_warps) {
+        const int r_lo = tile_reads(win_off, wtile_r0, tile, n_wtiles, R, sj, lane);
+        const long long w = tile * WT + lane * 4;
+        const int4 jj = *reinterpret_cast<const int4 *>(&sj[lane * 4]);
+        if (w + 4 <= W) {
+            const int4 v = __ldcs(reinterpret_cast<const int4 *>(win_node + w));   // streamed: keep the tables in L2
+            const uint4 rk = __ldcs(reinterpret_cast<const uint4 *>(win_rank + w));
+            const int jr[4] = {jj.x, jj.y, jj.z, jj.w};
+            const unsigned int sl[4] = {(unsigned int)v.x, (unsigned int)v.y, (unsigned int)v.z, (unsigned int)v.w};
+            const unsigned int rr[4] = {rk.x, rk.y, rk.z, rk.w};
+            uint2 inf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) inf[i] = nv.info[sl[i]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) raw[(size_t)inf[i].y + rr[i]] = (uint32_t)(r_lo + jr[i] + read_base);
+            __stcs(reinterpret_cast<int4 *>(win_node + w), make_int4((int)inf[0].x, (int)inf[1].x, (int)inf[2].x, (int)inf[3].x));
+        } else {
+            for (int i = 0; i < 4 && w + i < W; ++i) {
+                const uint2 inf = nv.info[(unsigned int)win_node[w + i]];
+                win_node[w + i] = (int)inf.x;
+                raw[(size_t)inf.y + win_rank[w + i]] = (uint32_t)(r_lo + sj[lane * 4 + i] + read_base);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// lazy removal of the equal neighbours the sort left (a gene-mer that occurs twice on one read): unique
+// counts -> offsets (scan), then one warp per node copies its list without them
+struct UniqLoad {
+    const int64_t *raw_off;
+    const uint32_t *dups;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const {
+        return (unsigned long long)(raw_off[i + 1] - raw_off[i]) - dups[i];
+    }
+};
+struct OffStore {
+    int64_t *off;
+    Cnt n;
+    long long *total;  // nullable
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        off[i] = (int64_t)excl;
+        if (total && i == n.get()) *total = (long long)excl;
+    }
+};
+
+__global__ void k_compact_unique(const int64_t *__restrict__ raw_off, const uint32_t *__restrict__ in,
+                                 const int64_t *__restrict__ out_off, uint32_t *__restrict__ out, const Cnt n_nodes) {
+    const long long N = n_nodes.get();
+    const int lane = threadIdx.x & 31;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long node = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; node < N; node += n_warps) {
+        const long long a = raw_off[node], n = raw_off[node + 1] - a;
+        long long o = out_off[node];
+        for (long long base = 0; base < n; base += 32) {
+            const long long i = base + lane;
+            uint32_t v = 0;
+            bool keep = false;
+            if (i < n) {
+                v = in[a + i];
+                keep = (i == 0) || in[a + i - 1] != v;
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, keep);
+            if (keep) out[o + __popc(m & ((1u << lane) - 1u))] = v;
+            o += __popc(m);
+        }
+    }
+}
+
+// ---- adjacency: forward list of node n = edges with source n and stored source direction +1, in edge
+// creation order (construct_graph.py:287-298); backward list likewise with -1.  Counting-sort transpose:
+// degrees (k_emit_edges / k_adj_count), scan, scatter through a cursor, segments sorted by edge index.
+__global__ void k_adj_count(const int32_t *__restrict__ e_src, const int8_t *__restrict__ e_sd, const Cnt n_edges,
+                            const Cnt n_nodes, unsigned long long *__restrict__ deg) {
+    const long long E = n_edges.get(), N = n_nodes.get();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride)
+        atomicAdd(&deg[e_src[e] + (e_sd[e] < 0 ? N : 0)], 1ull);
+}
+
+struct DegLoad {
+    const unsigned long long *deg;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return deg[i]; }
+};
+struct DegStore {
+    int64_t *adj_off;
+    unsigned long long *cursor;
+    Cnt n_nodes;
+    long long *sizes;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        adj_off[i] = (int64_t)excl;
+        cursor[i] = excl;
+        if (i == n_nodes.get()) sizes[SZ_FW] = (long long)excl;
+    }
+};
+
+__global__ void k_adj_scatter(const int32_t *__restrict__ e_src, const int8_t *__restrict__ e_sd, const Cnt n_edges,
+                              const Cnt n_nodes, unsigned long long *__restrict__ cursor, uint32_t *__restrict__ adj_edges) {
+    const long long E = n_edges.get(), N = n_nodes.get();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+        const unsigned long long pos = atomicAdd(&cursor[e_src[e] + (e_sd[e] < 0 ? N : 0)], 1ull);
+        adj_edges[pos] = (uint32_t)e;
+    }
+}
+
+// ---- components -------------------------------------------------------------------------------------
+// union-find over the emitted edges in first-seen order (each undirected adjacency once)
+__global__ void k_union_edges(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt, const Cnt n_edges,
+                              int32_t *__restrict__ parent) {
+    const long long E = n_edges.get();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+        const int s = e_src[e], t = e_tgt[e];
+        if (s < t) uf_union(parent, s, t);
+    }
+}
+
+// root of every node (read-only walk: the unions are over, trees are shallow thanks to the random
+// linking) and each component's first node (cmin starts at 0xFFFFFFFF)
+__global__ void k_cc_flatten(const int32_t *__restrict__ parent, const Cnt n_nodes, unsigned int *__restrict__ cmin,
+                             uint32_t *__restrict__ root) {
+    const long long N = n_nodes.get();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        int r = (int)i;
+        for (int p = parent[r]; p != r; p = parent[r]) r = p;
+        root[i] = (uint32_t)r;
+        // threads run roughly in index order: after the first few updates the minimum is final and the
+        // remaining nodes of a (giant) component skip the atomic
+        if ((unsigned int)i < ((volatile unsigned int *)cmin)[r]) atomicMin(&cmin[r], (unsigned int)i);
+    }
+}
+
+struct FirstLoad {
+    const uint32_t *root;
+    const unsigned int *cmin;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const {
+        return cmin[root[i]] == (unsigned int)i ? 1ull : 0ull;
+    }
+};
+struct FirstStore {
+    int *first_rank;
+    Cnt n;
+    long long *sizes;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        first_rank[i] = (int)excl;
+        if (i == n.get()) sizes[SZ_COMPS] = (long long)excl;
+    }
+};
+
+// component ids 1, 2, ... in order of each component's first node (construct_graph.py:920-927);
+// comp holds the roots on entry
+__global__ void k_cc_number(const unsigned int *__restrict__ cmin, const int *__restrict__ first_rank, const Cnt n_nodes,
+                            uint32_t *__restrict__ comp) {
+    const long long N = n_nodes.get();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        comp[i] = (uint32_t)first_rank[cmin[comp[i]]] + 1u;
+}
+
+// ---- filters (the host knows the sizes of the graph it filters; the sizes AFTER the filter stay on
+// the device) -----------------------------------------------------------------------------------------
+__global__ void k_component_max(const uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ comp,
+                                int64_t n_nodes, uint32_t *__restrict__ comp_max) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) {
+        // one giant component is the common case: read first, the maximum only ever grows
+        const uint32_t c = comp[i], v = node_cov[i];
+        if (v > ((volatile uint32_t *)comp_max)[c]) atomicMax(&comp_max[c], v);
+    }
+}
+
+// keep flags: mode 0 = coverage >= thr (filter_graph), mode 1 = component max >= thr
+__global__ void k_node_keep(const uint32_t *__restrict__ node_cov, const uint32_t *__restrict__ comp,
+                            const uint32_t *__restrict__ comp_max, int64_t n_nodes, uint32_t thr, int mode,
+                            int *__restrict__ keep) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) keep[i] = mode == 0 ? (node_cov[i] >= thr) : (comp_max[comp[i]] >= thr);
+    else if (i == n_nodes) keep[i] = 0;
+}
+
+__global__ void k_edge_keep(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt,
+                            const uint32_t *__restrict__ e_cov, const int *__restrict__ node_keep, int64_t n_edges,
+                            uint32_t thr, int *__restrict__ keep) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_edges) keep[e] = (e_cov[e] >= thr) && node_keep[e_src[e]] && node_keep[e_tgt[e]];
+    else if (e == n_edges) keep[e] = 0;
+}
+
+struct KeepLoad {
+    const int *keep;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return keep[i] ? 1ull : 0ull; }
+};
+struct KeepStore {
+    int *newidx;
+    long long n;
+    long long *total;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        newidx[i] = (int)excl;
+        if (i == n) *total = (long long)excl;
+    }
+};
+
+// upstream's remove_node dies with TypeError when a doomed node has two edges to one neighbour
+// (get_edge_hashes_between_nodes returns lists, construct_graph.py:383-386, 479-482)
+__global__ void k_multi_edge_check(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt,
+                                   const uint32_t *__restrict__ adj_edges, const int64_t *__restrict__ adj_off,
+                                   const int *__restrict__ node_keep, int64_t n_nodes, int *__restrict__ status) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes || node_keep[n]) return;
+    // the node's forward edges live at [adj_off[n], adj_off[n+1]), its backward ones at [adj_off[N+n], ...)
+    for (int pass = 0; pass < 2; ++pass) {
+        int64_t a0 = adj_off[n + pass * n_nodes], a1 = adj_off[n + pass * n_nodes + 1];
+        for (int64_t i = a0; i < a1; ++i) {
+            int32_t t = e_tgt[adj_edges[i]];
+            for (int pass2 = pass; pass2 < 2; ++pass2) {
+                int64_t b0 = pass2 == pass ? i + 1 : adj_off[n + n_nodes], b1 = adj_off[n + pass2 * n_nodes + 1];
+                for (int64_t j = b0; j < b1; ++j)
+                    if (e_tgt[adj_edges[j]] == t) status[ST_ERR] = AMIRA_E_MULTI_EDGE;
+            }
+        }
+    }
+}
+
+__global__ void k_compact_nodes(const int *__restrict__ keep, const int *__restrict__ newidx, int64_t n_nodes, int k,
+                                const int32_t *__restrict__ key_in, const uint32_t *__restrict__ cov_in,
+                                const int8_t *__restrict__ dir_in, const uint32_t *__restrict__ comp_in,
+                                const int64_t *__restrict__ roff_in, int32_t *__restrict__ key_out,
+                                uint32_t *__restrict__ cov_out, int8_t *__restrict__ dir_out,
+                                uint32_t *__restrict__ comp_out, int64_t *__restrict__ rcount_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes || !keep[i]) return;
+    const int o = newidx[i];
+    for (int j = 0; j < k; ++j) key_out[(int64_t)o * k + j] = key_in[i * k + j];
+    cov_out[o] = cov_in[i];
+    dir_out[o] = dir_in[i];
+    comp_out[o] = comp_in[i];
+    rcount_out[o] = roff_in[i + 1] - roff_in[i];
+}
+
+struct CountLoad {
+    const int64_t *cnt;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return (unsigned long long)cnt[i]; }
+};
+
+// one warp per surviving node copies its read list
+__global__ void k_compact_incidence(const int *__restrict__ keep, const int *__restrict__ newidx, int64_t n_nodes,
+                                    const int64_t *__restrict__ roff_in, const uint32_t *__restrict__ reads_in,
+                                    const int64_t *__restrict__ roff_out, uint32_t *__restrict__ reads_out) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_nodes || !keep[warp]) return;
+    const int64_t a = roff_in[warp], n = roff_in[warp + 1] - a, b = roff_out[newidx[warp]];
+    for (int64_t i = lane; i < n; i += 32) reads_out[b + i] = reads_in[a + i];
+}
+
+__global__ void k_compact_edges(const int *__restrict__ keep, const int *__restrict__ newidx,
+                                const int *__restrict__ node_newidx, int64_t n_edges,
+                                const int32_t *__restrict__ src_in, const int32_t *__restrict__ tgt_in,
+                                const int8_t *__restrict__ sd_in, const int8_t *__restrict__ td_in,
+                                const uint32_t *__restrict__ cov_in, int32_t *__restrict__ src_out,
+                                int32_t *__restrict__ tgt_out, int8_t *__restrict__ sd_out,
+                                int8_t *__restrict__ td_out, uint32_t *__restrict__ cov_out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges || !keep[e]) return;
+    const int o = newidx[e];
+    src_out[o] = node_newidx[src_in[e]];
+    tgt_out[o] = node_newidx[tgt_in[e]];
+    sd_out[o] = sd_in[e];
+    td_out[o] = td_in[e];
+    cov_out[o] = cov_in[e];
+}
+
+// remove_node_from_reads (construct_graph.py:442-461): windows of removed nodes become None and
+// their reads join _readsToCorrect.  One warp per 128-window tile; the read of a window is looked up
+// only in tiles that lose a window.
+__global__ void __launch_bounds__(256) k_mask_windows(const int *__restrict__ node_keep, const int *__restrict__ node_newidx,
+                                                      int32_t *__restrict__ win_node, int8_t *__restrict__ win_dir,
+                                                      const int64_t *__restrict__ win_off,
+                                                      const int32_t *__restrict__ wtile_r0, const long long R,
+                                                      int32_t *__restrict__ win_start, int32_t *__restrict__ win_end,
+                                                      const long long W, uint8_t *__restrict__ to_correct) {
+    __shared__ __align__(16) int s_j[8][WT];
+    const int lane = threadIdx.x & 31;
+    int *sj = s_j[threadIdx.x >> 5];
+    const long long n_wtiles = (W + WT - 1) / WT;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long tile = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; tile < n_wtiles; tile += n_warps) {
+        unsigned int gone = 0;  // bit i: window w0 + lane * 4 + i was removed now
+        const long long w = tile * WT + lane * 4;
+        for (int i = 0; i < 4 && w + i < W; ++i) {
+            const int n = win_node[w + i];
+            if (n < 0) continue;
+            if (node_keep[n]) {
+                win_node[w + i] = node_newidx[n];
+            } else {
+                win_node[w + i] = -1;
+                win_dir[w + i] = 0;
+                if (win_start) {
+                    win_start[w + i] = -1;
+                    win_end[w + i] = -1;
+                }
+                gone |= 1u << i;
+            }
+        }
+        if (__any_sync(0xffffffffu, gone != 0)) {
+            const int r_lo = tile_reads(win_off, wtile_r0, tile, n_wtiles, R, sj, lane);
+            for (int i = 0; i < 4; ++i)
+                if (gone & (1u << i)) to_correct[r_lo + sj[lane * 4 + i]] = 1;
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace amira

@@ -1,0 +1,360 @@
+// segsort.cuh -- ascending sort of every segment of a CSR value array.
+//
+// Two users in the GeneMerGraph build, both the second half of a counting-sort "transpose":
+//   node -> reads    Node.listOfReads is the ascending list of the reads that touch the node
+//                    (construct_node.py:64-67).  The insert kernel counts the windows per node and hands
+//                    every window its arrival rank; a scatter pass drops the window's read at
+//                    (segment start + rank); the segments are sorted here.  Equal neighbours after the
+//                    sort are windows of one read (counted per node, removed lazily -- they are rare).
+//   node -> edges    forward / backward edge lists in edge creation order (construct_graph.py:287-298).
+//
+// Segment sizes span five orders of magnitude (coverage-1 error nodes .. nodes on every read), so:
+//   n <= 1          copy
+//   n <= 8          one THREAD: 19-comparator network in registers (32 consecutive segments per warp)
+//   n <= 256        one WARP: bitonic network, 1..8 keys per lane in registers, shuffles for the
+//                   lane-crossing stages
+//   n <= 4096       one WARP: LSD radix sort, `match.any` ranking, per-warp digit counters in shared memory
+//   larger          one CTA: the same radix sort, 8 warps on contiguous chunks (any size)
+// The radix passes ping-pong between two global buffers A and B (segments are a few KB: the traffic stays
+// in L2).  Source and destination may differ (out of place: the source segments may even be laid out in a
+// different order, `a_start`), which decides the parity of the pass count: the last pass must land in the
+// destination.  Values are < 0xFFFFFFFF (read / edge indices are < 2^31); 0xFFFFFFFF pads.
+#pragma once
+
+#include "common.cuh"
+
+namespace amira {
+
+constexpr int SEG_BITONIC_MAX = 256;
+constexpr int SEG_WARP_MAX = 4096;
+constexpr int SEG_RADIX_THREADS = 256;
+constexpr int SEG_RADIX_WARPS = SEG_RADIX_THREADS / 32;
+constexpr int SEG_MAX_DIGIT_BITS = 11;
+constexpr uint32_t SEG_PAD = 0xFFFFFFFFu;
+
+// What to sort.  Segment s has n = off[s+1] - off[s] keys; it is read from a + (a_start ? a_start[s] : off[s])
+// and must end up at dst + off[s], where dst = (passes odd) ? b : a.
+struct SegJob {
+    uint32_t *a;
+    uint32_t *b;
+    const int64_t *off;
+    const uint32_t *a_start;  // nullable
+    const long long *n_seg_ptr;
+    int seg_mul;
+    int passes;      // radix passes (parity: see above)
+    int digit_bits;  // bits per radix pass
+    uint32_t *dups;                  // nullable: equal neighbours per segment after the sort
+    unsigned long long *total_dups;  // nullable
+};
+
+// work lists of the segments the main kernel defers to the radix kernel: [0] = number of warp-sized
+// segments, [1] = number of larger ones, then the segment ids (warp-sized from the front, larger from the back)
+struct SegWork {
+    unsigned int *counters;
+    long long *list;
+    long long cap;
+};
+
+__device__ __forceinline__ void ce(uint32_t &a, uint32_t &b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+// optimal 19-comparator network for 8 keys
+__device__ __forceinline__ void sort8(uint32_t (&v)[8]) {
+    ce(v[0], v[1]); ce(v[2], v[3]); ce(v[4], v[5]); ce(v[6], v[7]);
+    ce(v[0], v[2]); ce(v[1], v[3]); ce(v[4], v[6]); ce(v[5], v[7]);
+    ce(v[1], v[2]); ce(v[5], v[6]); ce(v[0], v[4]); ce(v[3], v[7]);
+    ce(v[1], v[5]); ce(v[2], v[6]);
+    ce(v[1], v[4]); ce(v[3], v[6]);
+    ce(v[2], v[4]); ce(v[3], v[5]);
+    ce(v[3], v[4]);
+}
+
+// bitonic sort of 32 * IPL keys held striped over a warp: element e = item * 32 + lane
+template <int IPL>
+__device__ __forceinline__ void warp_bitonic(uint32_t (&v)[IPL], const int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * IPL; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int dj = j >> 5;
+#pragma unroll
+                for (int it = 0; it < IPL; ++it) {
+                    if ((it & dj) == 0) {
+                        const bool asc = (it & (k >> 5)) == 0;
+                        const uint32_t a = v[it], b = v[it | dj];
+                        const bool sw = asc ? (a > b) : (a < b);
+                        v[it] = sw ? b : a;
+                        v[it | dj] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < IPL; ++it) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, v[it], j);
+                    const bool asc = (k >= 32) ? ((it & (k >> 5)) == 0) : ((lane & k) == 0);
+                    const bool lower = (lane & j) == 0;
+                    v[it] = (lower == asc) ? min(v[it], o) : max(v[it], o);
+                }
+            }
+        }
+    }
+}
+
+template <int IPL>
+__device__ __forceinline__ unsigned int warp_sort_segment(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                          const int n, const int lane) {
+    uint32_t v[IPL];
+#pragma unroll
+    for (int it = 0; it < IPL; ++it) {
+        const int e = it * 32 + lane;
+        v[it] = e < n ? src[e] : SEG_PAD;
+    }
+    warp_bitonic<IPL>(v, lane);
+    unsigned int dup = 0;
+#pragma unroll
+    for (int it = 0; it < IPL; ++it) {
+        const int e = it * 32 + lane;
+        // predecessor of element e: lane - 1 of the same item, or lane 31 of the previous item
+        uint32_t prev = __shfl_up_sync(0xffffffffu, v[it], 1);
+        if (it > 0) {
+            const uint32_t last = __shfl_sync(0xffffffffu, v[it - 1], 31);
+            if (lane == 0) prev = last;
+        }
+        if (e < n) {
+            dst[e] = v[it];
+            if (e > 0 && prev == v[it]) ++dup;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) dup += __shfl_xor_sync(0xffffffffu, dup, d);
+    return dup;
+}
+
+// Main pass: one warp per 32 consecutive segments; segments above SEG_BITONIC_MAX go to the work lists.
+__global__ void __launch_bounds__(256) k_segsort_main(const SegJob J, const SegWork work) {
+    const long long n_seg = *J.n_seg_ptr * J.seg_mul;
+    const int lane = threadIdx.x & 31;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    uint32_t *const dst_base = (J.passes & 1) ? J.b : J.a;
+    unsigned long long my_dups = 0;
+    for (long long base = ((((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 32; base < n_seg; base += n_warps * 32) {
+        const long long s = base + lane;
+        long long o = 0, n = 0, sa = 0;
+        if (s < n_seg) {
+            o = J.off[s];
+            n = J.off[s + 1] - o;
+            sa = J.a_start ? (long long)J.a_start[s] : o;
+        }
+        unsigned int d = 0;
+        if (n >= 1 && n <= 8) {
+            uint32_t v[8];
+            const uint32_t *src = J.a + sa;
+            uint32_t *dst = dst_base + o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = i < n ? src[i] : SEG_PAD;
+            sort8(v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < n) {
+                    dst[i] = v[i];
+                    if (i > 0 && v[i] == v[i - 1]) ++d;
+                }
+        } else if (n > SEG_BITONIC_MAX) {
+            const bool big = n > SEG_WARP_MAX;
+            const unsigned int pos = atomicAdd(&work.counters[big ? 1 : 0], 1u);
+            if ((long long)pos < work.cap) work.list[big ? work.cap - 1 - pos : pos] = s;
+        }
+        // segments of 9..256 keys: the whole warp sorts them one after the other
+        unsigned int mid = __ballot_sync(0xffffffffu, n > 8 && n <= SEG_BITONIC_MAX);
+        while (mid) {
+            const int l = __ffs(mid) - 1;
+            mid &= mid - 1;
+            const long long so = __shfl_sync(0xffffffffu, o, l), ssa = __shfl_sync(0xffffffffu, sa, l);
+            const int sn = (int)__shfl_sync(0xffffffffu, n, l);
+            const uint32_t *src = J.a + ssa;
+            uint32_t *dst = dst_base + so;
+            unsigned int sd;
+            if (sn <= 32) sd = warp_sort_segment<1>(src, dst, sn, lane);
+            else if (sn <= 64) sd = warp_sort_segment<2>(src, dst, sn, lane);
+            else if (sn <= 128) sd = warp_sort_segment<4>(src, dst, sn, lane);
+            else sd = warp_sort_segment<8>(src, dst, sn, lane);
+            if (lane == l) d = sd;
+        }
+        if (J.dups && s < n_seg) J.dups[s] = d;  // deferred segments are overwritten by the radix kernel
+        my_dups += d;
+    }
+    if (J.total_dups) {
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) my_dups += __shfl_xor_sync(0xffffffffu, my_dups, dd);
+        if (lane == 0 && my_dups) atomicAdd(J.total_dups, my_dups);
+    }
+}
+
+// ---- LSD radix sort ----------------------------------------------------------------------------------
+// One pass of one warp over keys src[0 .. n) (in order): stable scatter into dst by digit, with the
+// warp's running digit offsets in cnt[] (shared memory; on entry the exclusive start of every digit).
+__device__ __forceinline__ void radix_scatter(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const long long lo,
+                                              const long long hi, const int shift, const uint32_t mask,
+                                              unsigned int *cnt, const int lane) {
+    const unsigned int lt = (1u << lane) - 1u;
+    for (long long i0 = lo; i0 < hi; i0 += 32) {
+        const long long i = i0 + lane;
+        const bool valid = i < hi;
+        const uint32_t x = valid ? src[i] : 0u;
+        const uint32_t d = valid ? ((x >> shift) & mask) : SEG_PAD;
+        const unsigned int peers = __match_any_sync(0xffffffffu, d);
+        unsigned int start = 0;
+        if (valid) start = cnt[d];
+        __syncwarp();
+        if (valid) {
+            dst[start + __popc(peers & lt)] = x;
+            if ((peers & lt) == 0) cnt[d] = start + __popc(peers);  // first lane of the group moves the offset on
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void radix_count(const uint32_t *__restrict__ src, const long long lo, const long long hi,
+                                            const int shift, const uint32_t mask, unsigned int *cnt, const int lane) {
+    const unsigned int lt = (1u << lane) - 1u;
+    for (long long i0 = lo; i0 < hi; i0 += 32) {
+        const long long i = i0 + lane;
+        const bool valid = i < hi;
+        const uint32_t d = valid ? ((src[i] >> shift) & mask) : SEG_PAD;
+        const unsigned int peers = __match_any_sync(0xffffffffu, d);
+        if (valid && (peers & lt) == 0) cnt[d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ unsigned int count_dups(const uint32_t *__restrict__ x, const long long lo, const long long hi,
+                                                   const int lane_or_tid, const int stride) {
+    unsigned int d = 0;
+    for (long long i = lo + lane_or_tid; i < hi; i += stride)
+        if (i > 0 && x[i] == x[i - 1]) ++d;
+    return d;
+}
+
+__global__ void __launch_bounds__(SEG_RADIX_THREADS) k_segsort_radix(const SegJob J, const SegWork work) {
+    extern __shared__ unsigned int s_cnt[];  // [SEG_RADIX_WARPS][1 << digit_bits]
+    __shared__ unsigned int s_warp[SEG_RADIX_WARPS];
+    __shared__ unsigned int s_dup;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = 1 << J.digit_bits;
+    const uint32_t mask = (uint32_t)D - 1u;
+    unsigned int *cnt = s_cnt + warp * D;
+    const long long n_mid = min((long long)work.counters[0], work.cap);
+    const long long n_big = min((long long)work.counters[1], work.cap - n_mid);
+
+    // ---- warp-sized segments: one warp each
+    const long long n_warps = (long long)gridDim.x * SEG_RADIX_WARPS;
+    for (long long w = (long long)blockIdx.x * SEG_RADIX_WARPS + warp; w < n_mid; w += n_warps) {
+        const long long s = work.list[w];
+        const long long o = J.off[s], n = J.off[s + 1] - o;
+        uint32_t *buf[2] = {J.a + (J.a_start ? (long long)J.a_start[s] : o), J.b + o};
+        for (int pass = 0; pass < J.passes; ++pass) {
+            const uint32_t *src = buf[pass & 1];
+            uint32_t *dst = buf[(pass & 1) ^ 1];
+            const int shift = pass * J.digit_bits;
+            for (int i = lane; i < D; i += 32) cnt[i] = 0;
+            __syncwarp();
+            radix_count(src, 0, n, shift, mask, cnt, lane);
+            // exclusive scan of the D counters: each lane owns D/32 consecutive ones
+            {
+                const int per = D >> 5;  // D >= 32
+                unsigned int sum = 0;
+                for (int i = 0; i < per; ++i) sum += cnt[lane * per + i];
+                unsigned int incl = sum;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if (lane >= dd) incl += t;
+                }
+                unsigned int run = incl - sum;
+                for (int i = 0; i < per; ++i) {
+                    const unsigned int c = cnt[lane * per + i];
+                    cnt[lane * per + i] = run;
+                    run += c;
+                }
+            }
+            __syncwarp();
+            radix_scatter(src, dst, 0, n, shift, mask, cnt, lane);
+        }
+        if (J.dups) {
+            unsigned int d = count_dups(buf[J.passes & 1], 0, n, lane, 32);
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) d += __shfl_xor_sync(0xffffffffu, d, dd);
+            if (lane == 0) {
+                J.dups[s] = d;
+                if (d && J.total_dups) atomicAdd(J.total_dups, (unsigned long long)d);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- larger segments: the whole CTA, warp w on the w-th contiguous chunk
+    for (long long w = blockIdx.x; w < n_big; w += gridDim.x) {
+        const long long s = work.list[work.cap - 1 - w];
+        const long long o = J.off[s], n = J.off[s + 1] - o;
+        uint32_t *buf[2] = {J.a + (J.a_start ? (long long)J.a_start[s] : o), J.b + o};
+        const long long chunk = ((n + SEG_RADIX_WARPS - 1) / SEG_RADIX_WARPS + 31) & ~31ll;
+        const long long lo = min(n, warp * chunk), hi = min(n, lo + chunk);
+        for (int pass = 0; pass < J.passes; ++pass) {
+            const uint32_t *src = buf[pass & 1];
+            uint32_t *dst = buf[(pass & 1) ^ 1];
+            const int shift = pass * J.digit_bits;
+            for (int i = lane; i < D; i += 32) cnt[i] = 0;
+            __syncwarp();
+            radix_count(src, lo, hi, shift, mask, cnt, lane);
+            __syncthreads();
+            // digit d, warp w starts at (keys with smaller digits) + (keys with digit d in earlier warps):
+            // thread t owns the digits t * per .. + per - 1
+            {
+                const int per = max(1, D / SEG_RADIX_THREADS);
+                const int d0 = threadIdx.x * per;
+                unsigned int sum = 0;
+                if (d0 < D)
+                    for (int i = 0; i < per; ++i)
+                        for (int ww = 0; ww < SEG_RADIX_WARPS; ++ww) sum += s_cnt[ww * D + d0 + i];
+                unsigned int incl = sum;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if (lane >= dd) incl += t;
+                }
+                if (lane == 31) s_warp[warp] = incl;
+                __syncthreads();
+                unsigned int run = incl - sum;
+                for (int ww = 0; ww < warp; ++ww) run += s_warp[ww];
+                if (d0 < D)
+                    for (int i = 0; i < per; ++i)
+                        for (int ww = 0; ww < SEG_RADIX_WARPS; ++ww) {
+                            const unsigned int c = s_cnt[ww * D + d0 + i];
+                            s_cnt[ww * D + d0 + i] = run;
+                            run += c;
+                        }
+            }
+            __syncthreads();
+            radix_scatter(src, dst, lo, hi, shift, mask, cnt, lane);
+            __syncthreads();
+        }
+        if (J.dups) {
+            if (threadIdx.x == 0) s_dup = 0;
+            __syncthreads();
+            const unsigned int d = count_dups(buf[J.passes & 1], 0, n, threadIdx.x, SEG_RADIX_THREADS);
+            if (d) atomicAdd(&s_dup, d);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                J.dups[s] = s_dup;
+                if (s_dup && J.total_dups) atomicAdd(J.total_dups, (unsigned long long)s_dup);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace amira

@@ -226,13 +226,14 @@ __device__ __forceinline__ long long node_find_local(const BuildParams &L, bool 
 // its global node index, the global node its local coverage.  The probed table is the rank's own
 // L2-resident node table -- no table over the (much larger) global node set is ever built.
 __global__ void k_global_to_local(const BuildParams L, int n16, const NodeView nv, const int32_t *__restrict__ node_key,
-                                  long long n_global, uint32_t *__restrict__ cov_local) {
+                                  long long n_global, uint32_t *__restrict__ cov_local, uint32_t *__restrict__ node_src) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_global) return;
     const long long s = node_find_local(L, n16 != 0, node_key + j * L.k);
     if (s < 0) return;
     nv.a((unsigned int)s) = (unsigned int)j;
     cov_local[j] = nv.c((unsigned int)s) + 1u;
+    node_src[j] = nv.base((unsigned int)s);
 }
 
 // merged records -> the same offset in every rank's window (stores over NVLink, 4-byte granularity
@@ -330,17 +331,21 @@ __global__ void k_edge_ord_keys(const EdgeSlot *__restrict__ recs, long long n, 
     }
 }
 
-// directed edges per undirected record, in first-pair order (2, or 1 for a self edge)
-__global__ void k_edge_fanout(const unsigned int *__restrict__ perm, const EdgeSlot *__restrict__ recs, long long n,
-                              int *__restrict__ cnt) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
+// directed edges per undirected record, in first-pair order (2, or 1 for a self edge) -> offsets (scan functors)
+struct FanLoad {
+    const unsigned int *perm;
+    const EdgeSlot *recs;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const {
         const unsigned long long key = recs[perm[i]].key;
-        cnt[i] = ((unsigned int)(key >> 32) == (unsigned int)((key & 0xFFFFFFFFull) >> 1)) ? 1 : 2;
-    } else if (i == n) {
-        cnt[i] = 0;
+        return ((unsigned int)(key >> 32) == (unsigned int)((key & 0xFFFFFFFFull) >> 1)) ? 1ull : 2ull;
     }
-}
+};
+struct FanStore {
+    int *pref;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
+        pref[i] = (int)excl;
+    }
+};
 
 __global__ void k_emit_edges_sorted(const unsigned int *__restrict__ perm, const EdgeSlot *__restrict__ recs,
                                     const int *__restrict__ pref, long long n, int32_t *__restrict__ e_src,
@@ -368,10 +373,6 @@ __global__ void k_emit_edges_sorted(const unsigned int *__restrict__ perm, const
 __global__ void k_add_i32(int32_t *__restrict__ a, long long n, int32_t v) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] += v;
-}
-
-__global__ void k_set_w(const int64_t *__restrict__ win_off, int64_t R, long long *__restrict__ sizes) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) sizes[SZ_W] = win_off[R];
 }
 
 }  // namespace amira

@@ -49,8 +49,13 @@ class DeviceGraph:
     def reserve(self, n_nodes: int, n_edges: int):
         _lib.check(self._lib.amira_gmg_reserve(self._h, int(n_nodes), int(n_edges)))
 
-    def build(self, ids, off, k: int, pos_start=None, pos_end=None, on_device: bool = False):
-        """amira_gmg_build; ids/off are numpy arrays, torch tensors or raw pointers"""
+    def build(self, ids, off, k: int, pos_start=None, pos_end=None, on_device: bool = False, wait: bool = True):
+        """amira_gmg_build; ids/off are numpy arrays, torch tensors or raw pointers.
+
+        The library only enqueues the build; problems the device finds (a palindromic gene-mer, a table that
+        has to grow) surface at the first call that needs a result.  wait=True (default) asks for the early
+        sizes right away so that they surface here, as upstream's constructor raises; wait=False returns
+        as soon as the build is enqueued."""
         if isinstance(ids, np.ndarray):
             ids = np.ascontiguousarray(ids, np.int32)
             off = np.ascontiguousarray(off, np.int64)
@@ -62,6 +67,8 @@ class DeviceGraph:
         self.k, self.R, self.has_pos = int(k), int(R), pos_start is not None
         _lib.check(self._lib.amira_gmg_build(self._h, _ptr(ids), _ptr(off), R, int(k), _ptr(pos_start), _ptr(pos_end),
                                              int(on_device)))
+        if wait:
+            self.sizes_early()
         return self
 
     def build_resident(self, encoded, k: int, device: int | None = None):
@@ -116,6 +123,16 @@ class DeviceGraph:
     def debug_layout(self, mask: int):
         """test hook: 1 = no 16-byte node slots, 2 = no 16-byte edge slots, 4 = no packed keys"""
         _lib.check(self._lib.amira_gmg_debug_layout(self._h, int(mask)))
+
+    def debug_segsort(self, data, off, out_of_place=False, max_value=None):
+        """test hook: sort every segment data[off[s]:off[s+1]] ascending -> (sorted copy, equal neighbours per segment)"""
+        data = np.ascontiguousarray(data, np.uint32).copy()
+        off = np.ascontiguousarray(off, np.int64)
+        dups = np.zeros(len(off) - 1, np.uint32)
+        total = C.c_int64()
+        _lib.check(self._lib.amira_gmg_debug_segsort(self._h, _ptr(data), _ptr(off), len(off) - 1, _ptr(dups), C.byref(total),
+                                                     int(out_of_place), int(data.max()) + 1 if max_value is None and len(data) else int(max_value or 2)))
+        return data, dups, total.value
 
     def atomic_peak(self, table_bytes: int, n_ops: int):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

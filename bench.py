@@ -247,7 +247,7 @@ def run_gpu(args):
 
     # ---- device-resident arm ------------------------------------------------------------------
     def step_device():
-        dg.build(d_ids, d_off, k, on_device=True)
+        dg.build(d_ids, d_off, k, on_device=True, wait=False)     # enqueue only: no host synchronisation per build
 
     if args.table_load > 0:              # developer experiment: hash-table load factor
         step_device()
@@ -408,11 +408,11 @@ def run_gpu(args):
             di, do = torch.from_numpy(i2).cuda(), torch.from_numpy(o2).cuda()
         stream.synchronize()
         for _ in range(5):
-            dg.build(di, do, c2.k, on_device=True)
+            dg.build(di, do, c2.k, on_device=True, wait=False)
         dg.sync()
         e0.record(stream)
         for _ in range(20):
-            dg.build(di, do, c2.k, on_device=True)
+            dg.build(di, do, c2.k, on_device=True, wait=False)
         e1.record(stream)
         torch.cuda.synchronize()
         w2 = synth.count_windows(o2, c2.k)
@@ -445,6 +445,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-atomic-peak", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (profiling runs)")
     ap.add_argument("--table-load", type=float, default=0.0, help="experiment: hash tables sized to this load factor")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

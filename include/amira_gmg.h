@@ -163,6 +163,13 @@ int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int 
  * 16-byte edge slots, 4 = no packed keys (gene-mers compared through the ids array). */
 int amira_gmg_debug_layout(amira_gmg *h, int mask);
 
+/* Test hook: the segmented sort behind the node -> reads and node -> edges lists, on host arrays:
+ * data[off[s] .. off[s+1]) is sorted ascending for every s < n_seg (values < max_value); dups[s] (nullable)
+ * receives the number of equal neighbours in segment s, *total_dups their sum.  out_of_place != 0 runs the
+ * variant that reads the segments from a differently ordered source buffer (odd number of radix passes). */
+int amira_gmg_debug_segsort(amira_gmg *h, uint32_t *data, const int64_t *off, int64_t n_seg, uint32_t *dups,
+                            int64_t *total_dups, int out_of_place, int64_t max_value);
+
 /* Micro-benchmark for the atomic roofline: random-address 32-bit RED.ADD, 64-bit CAS
  * and (if load_per_s is non-NULL) 32-byte sector loads into a table of table_bytes; returns
  * operations per second of each. */

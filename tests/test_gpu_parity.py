@@ -276,3 +276,73 @@ def test_gpu_random_small_inputs(dg):
         dg.filter_graph(a, b)
         assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], seed
     assert n_pal > 0 and n_multi >= 0
+
+
+@pytest.mark.parametrize("out_of_place", [False, True])
+@pytest.mark.parametrize("vmax", [40, 2_000_000, 2**31 - 2])
+def test_gpu_segmented_sort_all_size_classes(dg, out_of_place, vmax):
+    """the sort behind node -> reads / node -> edges: thread (<= 8), warp bitonic (<= 256), warp radix (<= 4096) and
+    CTA radix (larger) segments, in place and out of place, with duplicates, against numpy"""
+    rng = np.random.default_rng(11)
+    sizes = np.concatenate([rng.integers(0, 10, 3000), rng.integers(0, 70, 2000), rng.integers(60, 520, 300),
+                            [0, 1, 2, 8, 9, 31, 32, 33, 64, 65, 128, 129, 256, 257, 511, 512, 513, 1024, 1025, 4095, 4096,
+                             4097, 5000, 16385, 40000, 70001], rng.integers(0, 10, 500)])
+    rng.shuffle(sizes)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    data = rng.integers(0, vmax + 1, off[-1]).astype(np.uint32)
+    small_range = rng.random(len(sizes)) < 0.3                      # many duplicates in some segments
+    for s in np.flatnonzero(small_range):
+        data[off[s]:off[s + 1]] %= 50
+    got, dups, total = dg.debug_segsort(data, off, out_of_place=out_of_place, max_value=vmax + 1)
+    want = data.copy()
+    want_dups = np.zeros(len(sizes), np.uint32)
+    for s in range(len(sizes)):
+        seg = np.sort(data[off[s]:off[s + 1]])
+        want[off[s]:off[s + 1]] = seg
+        want_dups[s] = int(np.count_nonzero(seg[1:] == seg[:-1]))
+    assert np.array_equal(got, want)
+    assert np.array_equal(dups, want_dups) and total == int(want_dups.sum())
+
+
+def test_gpu_repeated_genemers_and_heavy_nodes(dg):
+    """a gene-mer twice on one read (duplicate incidences are removed, coverage counts both) and nodes that lie
+    on more reads than a CTA sorts in shared memory"""
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    rng = np.random.default_rng(3)
+    reads = []
+    for i in range(20000):                                   # every read carries (1,2,3[,4]) -> nodes on 20000 reads
+        tail = (rng.integers(5, 400, rng.integers(0, 6)) * rng.choice([-1, 1])).tolist()
+        core = [1, 2, 3, 4]
+        if i % 7 == 0:
+            core = core + [9] + core                          # the same gene-mers twice on this read
+        if i % 2:
+            core = [-g for g in reversed(core)]
+        reads.append(core + tail if i % 3 else tail + core)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    ids = np.concatenate([np.asarray(r, np.int32) for r in reads])
+    for k in (3, 5):
+        ref = c_oracle.COracleGraph(ids, off, k)
+        dg.build(ids, off, k)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], k
+        ref.filter_graph(3, 2)
+        dg.filter_graph(3, 2)
+        assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], k
+
+
+def test_gpu_key_width_boundary_values(dg):
+    """ids at the edge of the remembered key width (|id| = 2^(b-1) - 2 fits, -(2^(b-1) - 1) and -2^(b-1) must not be
+    packed with b bits): the handle first sees V = 14, then ids that only use the two values beyond"""
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    rng = np.random.default_rng(9)
+    off = np.arange(0, 1201, 12).astype(np.int64)
+    small = (rng.integers(1, 15, off[-1]) * rng.choice([-1, 1], off[-1])).astype(np.int32)
+    for k in (3, 5):
+        dg.build(small, off, k)
+        assert O.diff_arrays(dg.arrays(), c_oracle.COracleGraph(small, off, k).arrays()) == []
+        for vals in ([-15, -16, 2, 3], [-16, 16, 15, -15], [14, -14, 1], [-31, -32, 30, 2]):
+            ids = rng.choice(np.asarray(vals, np.int32), off[-1]).astype(np.int32)
+            ids[::12] = 1                                    # no palindromes at even k, some structure
+            dg.build(ids, off, k)
+            assert O.diff_arrays(dg.arrays(), c_oracle.COracleGraph(ids, off, k).arrays()) == [], (k, vals)
