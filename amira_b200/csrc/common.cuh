@@ -183,6 +183,22 @@ bool comm_p2p(const Comm *c);
 void *comm_window(const Comm *c, int p);
 int comm_barrier(Comm *c, cudaStream_t st);
 
+// L2 eviction-priority hints: the small, randomly revisited arrays (hash tables, slot info, the write frontier
+// of the raw read lists) are kept with evict_last while the window arrays stream past with evict_first loads
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_u32_hint(uint32_t *p, uint32_t v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint2 ld_u32x2_hint(const uint2 *p, unsigned long long pol) {
+    uint2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33;
     x *= 0xff51afd7ed558ccdULL;

@@ -71,9 +71,10 @@ struct amira_gmg {
     int64_t cache_R = -1, cache_G = 0;
 
     // per read / per tile
-    DevBuf win_off, is_short, to_correct, tile_r0, wtile_r0;
+    DevBuf win_off, is_short, to_correct, tile_r0;
     // per window
-    DevBuf win_node, win_dir, win_rank, win_start, win_end;
+    DevBuf win_slot, win_node, win_dir, win_rank, win_read, win_start, win_end;  // win_slot: table slots from the insert kernel; win_node: node indices
+    int64_t scatter_l2_bytes = 40ll << 20;  // raw read lists one scatter pass may touch (stays in L2)
     // hash tables + first-seen bitmaps
     DevBuf ntab, etab, slot_info, node_src, bitmaps, cnt_node, cnt_edge;
     unsigned int ncap = 0, ecap = 0;
@@ -107,6 +108,24 @@ struct amira_gmg {
     bool pending_is_build = false;
     int attempts = 0;
     int last_status = AMIRA_OK;
+
+    // A build whose input pointers, sizes and table capacities repeat (the k sweep / rebuild loop over a resident
+    // CSR, the small-graph regime where ~50 launches cost more than the kernels) is captured into a CUDA graph the
+    // second time it is seen and replayed from then on.
+    struct GraphKey {
+        const void *ids, *off, *ps, *pe;
+        int64_t R, G, cap_nodes, cap_edges;
+        unsigned int ncap, ecap;
+        int k, key_bits, layout;
+        bool operator==(const GraphKey &o) const {
+            return ids == o.ids && off == o.off && ps == o.ps && pe == o.pe && R == o.R && G == o.G && cap_nodes == o.cap_nodes &&
+                   cap_edges == o.cap_edges && ncap == o.ncap && ecap == o.ecap && k == o.k && key_bits == o.key_bits && layout == o.layout;
+        }
+    };
+    GraphKey graph_key = {}, last_key = {};
+    cudaGraphExec_t graph_exec = nullptr;
+    bool capturing = false;
+    int64_t graph_launches = 0, graph_kernels = 0;  // replays; kernels inside the captured graph
 
     bool profiling = false;
     cudaEvent_t ev[AMIRA_PH_COUNT][2] = {};
@@ -229,9 +248,13 @@ int run_segsort(amira_gmg *h, uint32_t *a, uint32_t *b, const int64_t *off, cons
     J.digit_bits = std::max(5, (bits + J.passes - 1) / J.passes);
     const int grid_main = (int)std::min<int64_t>(grid_for(seg_max, 256), (int64_t)h->n_sm * 8);
     LAUNCH(h, k_segsort_main, grid_main, 256, J, work);
-    const size_t smem = sizeof(unsigned int) * SEG_RADIX_WARPS * ((size_t)1 << J.digit_bits);
-    const int grid_rad = (int)std::min<int64_t>(cap, (int64_t)h->n_sm * (smem > 32768 ? 3 : 6));
-    k_segsort_radix<<<grid_rad, SEG_RADIX_THREADS, smem, h->cur>>>(J, work);
+    LAUNCH(h, k_segsort_warp, (int)std::min<int64_t>((cap + 3) / 4, (int64_t)h->n_sm * 4), 128, J, work);
+    // shared memory: the digit counters of 8 warps + two key buffers (8192 keys each when they fit ~72 KB)
+    const size_t cnt_bytes = sizeof(unsigned int) * SEG_RADIX_WARPS * ((size_t)1 << J.digit_bits);
+    const int kcap = 0;  // everything that fits shared memory is sorted by k_segsort_warp
+    const size_t smem = cnt_bytes + 2 * sizeof(uint32_t) * (size_t)kcap;
+    const int grid_rad = (int)std::min<int64_t>(cap, (int64_t)h->n_sm * 3);
+    k_segsort_radix<<<grid_rad, SEG_RADIX_THREADS, smem, h->cur>>>(J, work, kcap);
     h->launches++;
     AMIRA_CUDA(cudaGetLastError());
     return AMIRA_OK;
@@ -323,10 +346,11 @@ int plan_build(amira_gmg *h) {
     AMIRA_TRY(h->is_short.reserve(R + 1));
     AMIRA_TRY(h->to_correct.reserve(R + 1));
     AMIRA_TRY(h->tile_r0.reserve(sizeof(int32_t) * (n_tiles + 1)));
-    AMIRA_TRY(h->wtile_r0.reserve(sizeof(int32_t) * (G / WT + 2)));
-    AMIRA_TRY(h->win_node.reserve(sizeof(int32_t) * gcap + 16));
+    AMIRA_TRY(h->win_slot.reserve(sizeof(int32_t) * gcap + 32));
+    AMIRA_TRY(h->win_node.reserve(sizeof(int32_t) * gcap + 32));
     AMIRA_TRY(h->win_dir.reserve(gcap));
-    AMIRA_TRY(h->win_rank.reserve(sizeof(uint32_t) * gcap + 16));
+    AMIRA_TRY(h->win_rank.reserve(sizeof(uint32_t) * gcap + 32));
+    AMIRA_TRY(h->win_read.reserve(sizeof(int32_t) * gcap + 32));
     if (h->has_pos) {
         AMIRA_TRY(h->win_start.reserve(sizeof(int32_t) * gcap));
         AMIRA_TRY(h->win_end.reserve(sizeof(int32_t) * gcap));
@@ -378,7 +402,7 @@ int enqueue_report(amira_gmg *h, int which) {
                                h->stream));
     AMIRA_CUDA(cudaMemcpyAsync(h->h_sizes + which * SZ_COUNT, h->d_sizes.p, sizeof(long long) * SZ_COUNT,
                                cudaMemcpyDeviceToHost, h->stream));
-    AMIRA_CUDA(cudaEventRecord(which ? h->ev_done : h->ev_early, h->stream));
+    if (!h->capturing) AMIRA_CUDA(cudaEventRecord(which ? h->ev_done : h->ev_early, h->stream));  // (a replayed graph: recorded after the launch)
     h->lib_launches += 2;
     return AMIRA_OK;
 }
@@ -398,7 +422,7 @@ int enqueue_insert(amira_gmg *h) {
                h->is_short.as<uint8_t>(), h->to_correct.as<uint8_t>(), h->tile_r0.as<int32_t>(),
                h->d_sizes.as<long long>(), h->d_status.as<int>());
         AMIRA_TRY(run_scan(h, WinOffLoad{h->win_off.as<int64_t>()},
-                           WinOffStore{h->win_off.as<int64_t>(), h->wtile_r0.as<int32_t>(), R, dsz(h, 0)}, nullptr, 1, R, R));
+                           WinOffStore{h->win_off.as<int64_t>(), R, dsz(h, 0)}, nullptr, 1, R, R));
     }
     Phase ph(h, AMIRA_PH_INSERT);
     const size_t nbytes = h->n16 ? (sizeof(NodeSlot16) + sizeof(unsigned int)) * (size_t)h->ncap : sizeof(NodeSlot) * (size_t)h->ncap;
@@ -414,8 +438,9 @@ int enqueue_insert(amira_gmg *h) {
     P.tile_lo = 0; P.tile_hi = n_tiles;
     P.ntab = h->ntab.as<NodeSlot>(); P.ntab16 = h->ntab.as<NodeSlot16>(); P.ncov = h->nview.cov;
     P.ncap = h->ncap; P.etab = h->etab.as<EdgeSlot>(); P.etab16 = h->etab.as<EdgeSlot16>(); P.ecap = h->ecap;
-    P.win_node = h->win_node.as<int32_t>(); P.win_dir = h->win_dir.as<int8_t>();
+    P.win_node = h->win_slot.as<int32_t>(); P.win_dir = h->win_dir.as<int8_t>();
     P.win_rank = h->win_rank.as<uint32_t>();
+    P.win_read = h->win_read.as<int32_t>();
     P.win_start = h->has_pos ? h->win_start.as<int32_t>() : nullptr;
     P.win_end = h->has_pos ? h->win_end.as<int32_t>() : nullptr;
     P.status = h->d_status.as<int>();
@@ -544,12 +569,18 @@ int enqueue_tail(amira_gmg *h) {
             Phase ph(h, AMIRA_PH_REMAP);
             AMIRA_TRY(run_scan(h, CovLoad{cov}, CovStore{h->reads_off.as<int64_t>(), N, dsz(h, 0)}, dsz(h, SZ_NODES), 1, 0,
                                h->cap_nodes));
-            LAUNCH(h, k_scatter_windows, (int)std::min<int64_t>(grid_for((G + WT - 1) / WT * 32, 256), (int64_t)h->n_sm * 8), 256,
-                   h->nview, h->win_node.as<int32_t>(), h->win_rank.as<uint32_t>(), h->win_off.as<int64_t>(),
-                   h->wtile_r0.as<int32_t>(), (const long long *)h->d_sizes.p, (long long)h->R, h->reads_tmp.as<uint32_t>(),
-                   (int32_t)h->first_read_global);
+            // one pass per slot range whose raw lists fit L2 (see k_scatter_windows); the first one also writes the
+            // per-read node lists into the second window array
+            const int n_pass = (int)std::min<int64_t>(8, std::max<int64_t>(1, (4 * G + h->scatter_l2_bytes - 1) / h->scatter_l2_bytes));
+            const int sgrid = (int)std::min<int64_t>(grid_for((G + 3) / 4, 256), (int64_t)h->n_sm * 16);
+            for (int p = 0; p < n_pass; ++p) {
+                const unsigned int lo = (unsigned int)((uint64_t)h->ncap * p / n_pass), hi = (unsigned int)((uint64_t)h->ncap * (p + 1) / n_pass);
+                LAUNCH(h, k_scatter_windows, sgrid, 256, h->nview, h->win_slot.as<int32_t>(),
+                       p == 0 ? h->win_node.as<int32_t>() : (int32_t *)nullptr, h->win_rank.as<uint32_t>(),
+                       h->win_read.as<int32_t>(), (const long long *)h->d_sizes.p, h->reads_tmp.as<uint32_t>(), lo, hi);
+            }
         }
-        AMIRA_CUDA(cudaEventRecord(h->ev_reads_ready, st));
+        if (!h->capturing) AMIRA_CUDA(cudaEventRecord(h->ev_reads_ready, st));
         Phase ph(h, AMIRA_PH_INCIDENCE);
         const int64_t reads_global = h->world > 1 ? 0x7FFFFFF0ll : h->R;
         AMIRA_TRY(run_segsort(h, h->reads_tmp.as<uint32_t>(), h->reads.as<uint32_t>(), h->reads_off.as<int64_t>(),
@@ -575,6 +606,52 @@ int do_build(amira_gmg *h) {
     if (h->world == 1) {
         AMIRA_TRY(plan_build(h));
         AMIRA_TRY(reserve_graph(h, h->ncap, 2 * (int64_t)h->ecap));
+        const amira_gmg::GraphKey key{h->ids, h->off, h->ps, h->pe, h->R, h->G, h->cap_nodes, h->cap_edges, h->ncap, h->ecap,
+                                      h->k, h->key_bits, (h->n16 ? 1 : 0) | (h->e16 ? 2 : 0)};
+        static const bool no_graph = getenv("AMIRA_NO_GRAPH") != nullptr;
+        const bool can_graph = h->input_on_device && !h->profiling && h->n_pieces == 0 && h->G <= (64ll << 20) && !no_graph;
+        auto after_launch = [&]() -> int {
+            AMIRA_CUDA(cudaEventRecord(h->ev_reads_ready, st));
+            AMIRA_CUDA(cudaEventRecord(h->ev_early, st));
+            AMIRA_CUDA(cudaEventRecord(h->ev_done, st));
+            h->pending = 2;
+            h->pending_is_build = true;
+            h->graph_launches++;
+            return AMIRA_OK;
+        };
+        if (can_graph && h->graph_exec && key == h->graph_key) {
+            AMIRA_CUDA(cudaGraphLaunch(h->graph_exec, st));
+            h->launches += h->graph_kernels;
+            return after_launch();
+        }
+        if (can_graph && key == h->last_key) {
+            if (h->graph_exec) {
+                cudaGraphExecDestroy(h->graph_exec);
+                h->graph_exec = nullptr;
+            }
+            AMIRA_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            h->capturing = true;
+            const int64_t launches0 = h->launches;
+            int rc = enqueue_insert(h);
+            if (rc == AMIRA_OK) rc = enqueue_order(h);
+            if (rc == AMIRA_OK) rc = enqueue_tail(h);
+            h->capturing = false;
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc == AMIRA_OK && ce == cudaSuccess && graph) {
+                if (cudaGraphInstantiate(&h->graph_exec, graph, 0) != cudaSuccess) h->graph_exec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            if (h->graph_exec) {
+                h->graph_key = key;
+                h->graph_kernels = h->launches - launches0;
+                AMIRA_CUDA(cudaGraphLaunch(h->graph_exec, st));
+                return after_launch();
+            }
+            cudaGetLastError();  // capture failed: fall through to the plain launches
+            h->pending = 0;
+        }
+        h->last_key = key;
         AMIRA_TRY(enqueue_insert(h));
         AMIRA_TRY(enqueue_order(h));
         return enqueue_tail(h);
@@ -786,10 +863,10 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
                h->e_cov2.as<uint32_t>());
     }
     if (W > 0) {
-        LAUNCH(h, k_mask_windows, (int)std::min<int64_t>(grid_for((W + WT - 1) / WT * 32, 256), (int64_t)h->n_sm * 8), 256, keep_n,
-               new_n, h->win_node.as<int32_t>(), h->win_dir.as<int8_t>(), h->win_off.as<int64_t>(), h->wtile_r0.as<int32_t>(),
-               (long long)h->R, h->has_pos ? h->win_start.as<int32_t>() : nullptr,
-               h->has_pos ? h->win_end.as<int32_t>() : nullptr, (long long)W, h->to_correct.as<uint8_t>());
+        LAUNCH(h, k_mask_windows, (int)std::min<int64_t>(grid_for(W, 256), (int64_t)h->n_sm * 32), 256, keep_n, new_n,
+               h->win_node.as<int32_t>(), h->win_dir.as<int8_t>(), h->win_read.as<int32_t>(), (int32_t)h->first_read_global,
+               h->has_pos ? h->win_start.as<int32_t>() : nullptr, h->has_pos ? h->win_end.as<int32_t>() : nullptr,
+               (long long)W, h->to_correct.as<uint8_t>());
     }
     AMIRA_CUDA(cudaEventRecord(h->ev_reads_ready, h->stream));
     std::swap(h->node_key, h->node_key2);
@@ -1242,6 +1319,8 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     cudaDeviceProp prop;
     AMIRA_CUDA(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
+    if (prop.l2CacheSize > 0) h->scatter_l2_bytes = std::max<int64_t>(8ll << 20, (int64_t)prop.l2CacheSize / 3);
+    if (const char *e = getenv("AMIRA_SCATTER_MB")) h->scatter_l2_bytes = std::max<int64_t>(1, atoll(e)) << 20;  // developer experiments
     int occ = 1;
     AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_insert_windows<5, true, true>), INS_THREADS, 0));
     h->insert_ctas_per_sm = std::max(1, occ);
@@ -1251,8 +1330,7 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     AMIRA_CUDA(cudaMallocHost((void **)&h->h_sizes, sizeof(long long) * 2 * SZ_COUNT));
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
-    AMIRA_CUDA(cudaFuncSetAttribute(k_segsort_radix, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sizeof(unsigned int) * SEG_RADIX_WARPS << SEG_MAX_DIGIT_BITS)));
+    AMIRA_CUDA(cudaFuncSetAttribute(k_segsort_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 2 * 4 * SEG_STAGE_MAX));
     for (int i = 0; i < AMIRA_PH_COUNT; ++i)
         for (int j = 0; j < 2; ++j) AMIRA_CUDA(cudaEventCreate(&h->ev[i][j]));
     *out = h;
@@ -1278,12 +1356,12 @@ void amira_gmg_destroy(amira_gmg *h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     DevBuf *bufs[] = {&h->d_ids, &h->d_off, &h->d_ps, &h->d_pe, &h->win_off, &h->is_short, &h->to_correct, &h->tile_r0,
-                      &h->win_node, &h->win_dir, &h->wtile_r0, &h->win_start, &h->win_end, &h->ntab, &h->etab,
+                      &h->win_node, &h->win_dir, &h->win_read, &h->win_start, &h->win_end, &h->ntab, &h->etab,
                       &h->bitmaps, &h->cnt_node, &h->cnt_edge, &h->node_key, &h->node_cov, &h->node_dir, &h->node_comp,
                       &h->reads_off, &h->reads, &h->node_key2, &h->node_cov2, &h->node_dir2, &h->node_comp2,
                       &h->reads_off2, &h->reads2, &h->parent, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
                       &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
-                      &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->node_src, &h->win_rank, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->dups,
+                      &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->node_src, &h->win_rank, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->dups,
                       &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,
                       &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rkey2, &h->x_rmeta2,
                       &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_sortk, &h->x_sortk2, &h->x_sorti,
@@ -1292,6 +1370,7 @@ void amira_gmg_destroy(amira_gmg *h) {
     for (DevBuf *b : bufs) b->release();
     if (h->comm) comm_destroy(h->comm);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->ev_early) cudaEventDestroy(h->ev_early);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->h_status) cudaFreeHost(h->h_status);

@@ -19,7 +19,6 @@ struct Cnt {
     __device__ __forceinline__ long long get() const { return p ? *p : v; }
 };
 
-constexpr int WT = 128;  // windows per tile of the window -> read map
 
 __global__ void k_fill_u32(uint32_t *__restrict__ a, const Cnt n, const long long mul, const long long add, const uint32_t v) {
     const long long m = n.get() * mul + add;
@@ -35,61 +34,20 @@ __global__ void k_fill_u64(unsigned long long *__restrict__ a, const Cnt n, cons
 }
 
 // ---- per-read window offsets (scan functors) ---------------------------------------------------
-// win_off = exclusive scan of the per-read window counts (in place); every read also records itself as
-// the owner of each 128-window tile whose first window it holds (the window -> read map of the passes
-// that walk the windows: nothing stores a read index per window)
+// win_off = exclusive scan of the per-read window counts (in place)
 struct WinOffLoad {
     const int64_t *nwin;
     __device__ __forceinline__ unsigned long long operator()(long long i) const { return (unsigned long long)nwin[i]; }
 };
 struct WinOffStore {
     int64_t *win_off;
-    int32_t *wtile_r0;
     long long R;
     long long *sizes;
-    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long val) const {
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
         win_off[i] = (int64_t)excl;
-        const long long a = (long long)excl, b = a + (long long)val;
-        for (long long t = (a + WT - 1) / WT; t * WT < b; ++t) wtile_r0[t] = (int32_t)i;
-        if (i == R) sizes[SZ_W] = a;
+        if (i == R) sizes[SZ_W] = (long long)excl;
     }
 };
-
-// Which read each of the 128 windows of tile `tile` belongs to, relative to the tile's first read
-// (returned): sj[0..128) per warp.  Reads without windows own nothing and are skipped by construction.
-__device__ __forceinline__ int tile_reads(const int64_t *__restrict__ win_off, const int32_t *__restrict__ wtile_r0,
-                                          const long long tile, const long long n_wtiles, const long long R,
-                                          int *sj, const int lane) {
-    const long long w0 = tile * WT;
-    const int r_lo = wtile_r0[tile];
-    const int r_hi = (tile + 1 < n_wtiles) ? wtile_r0[tile + 1] : (int)(R - 1);
-    *reinterpret_cast<int4 *>(&sj[lane * 4]) = make_int4(0, 0, 0, 0);
-    __syncwarp();
-    for (int j = 1 + lane; j <= r_hi - r_lo; j += 32) {
-        const long long o = win_off[r_lo + j] - w0;
-        if (o < WT) atomicMax(&sj[(int)o], j);
-    }
-    __syncwarp();
-    int4 v = *reinterpret_cast<int4 *>(&sj[lane * 4]);
-    v.y = max(v.x, v.y);
-    v.z = max(v.y, v.z);
-    v.w = max(v.z, v.w);
-    int incl = v.w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl = max(incl, o);
-    }
-    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 0;
-    v.x = max(v.x, excl);
-    v.y = max(v.y, excl);
-    v.z = max(v.z, excl);
-    v.w = max(v.w, excl);
-    *reinterpret_cast<int4 *>(&sj[lane * 4]) = v;
-    __syncwarp();
-    return r_lo;
-}
 
 // ---- first-seen order ---------------------------------------------------------------------------
 // bit p of bm_node is set iff a node was first seen at call p; bm_ea likewise for undirected edge
@@ -288,42 +246,57 @@ struct CovStore {
     }
 };
 
-__global__ void __launch_bounds__(256) k_scatter_windows(const NodeView nv, int32_t *__restrict__ win_node,
+// One thread per window, four windows per thread: slot -> (node index, start of the slot's raw list) in one 8-byte
+// gather, the read goes to raw[start + arrival rank], the node index to the per-read list.  The insert kernel left
+// slot, rank and read per window, so the pass is streamed loads, one gather, one scattered store and one streamed
+// store (deriving the read from the offsets instead costs more than the 4 bytes it saves).
+// The raw lists are laid out in table (slot) order, so a slot range is a contiguous piece of `raw`, and the random
+// 4-byte stores only merge into full sectors while that piece stays in L2 (C5 shard, 130 MB of raw lists in one
+// pass: 770 MB of DRAM writes for 260 MB of payload).  So the host runs the pass once per slot range
+// [slot_lo, slot_hi) that fits L2; the pass with node_out != nullptr also writes the per-read node lists (to a
+// second array: the later passes still need the slots).
+__global__ void __launch_bounds__(256) k_scatter_windows(const NodeView nv, const int32_t *__restrict__ win_slot,
+                                                         int32_t *__restrict__ node_out,
                                                          const uint32_t *__restrict__ win_rank,
-                                                         const int64_t *__restrict__ win_off,
-                                                         const int32_t *__restrict__ wtile_r0,
-                                                         const long long *__restrict__ sizes, const long long R,
-                                                         uint32_t *__restrict__ raw, const int32_t read_base) {
-    __shared__ __align__(16) int s_j[8][WT];
-    const int lane = threadIdx.x & 31;
-    int *sj = s_j[threadIdx.x >> 5];
+                                                         const int32_t *__restrict__ win_read,
+                                                         const long long *__restrict__ sizes,
+                                                         uint32_t *__restrict__ raw, const unsigned int slot_lo,
+                                                         const unsigned int slot_hi) {
     const long long W = sizes[SZ_W];
-    const long long n_wtiles = (W + WT - 1) / WT;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long tile = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; tile < n_wtiles; tile += n_warps) {
-        const int r_lo = tile_reads(win_off, wtile_r0, tile, n_wtiles, R, sj, lane);
-        const long long w = tile * WT + lane * 4;
-        const int4 jj = *reinterpret_cast<const int4 *>(&sj[lane * 4]);
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    const unsigned int span = slot_hi - slot_lo;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; w < W; w += stride) {
         if (w + 4 <= W) {
-            const int4 v = __ldcs(reinterpret_cast<const int4 *>(win_node + w));   // streamed: keep the tables in L2
-            const uint4 rk = __ldcs(reinterpret_cast<const uint4 *>(win_rank + w));
-            const int jr[4] = {jj.x, jj.y, jj.z, jj.w};
+            const int4 v = __ldcs(reinterpret_cast<const int4 *>(win_slot + w));   // streamed: keep the tables in L2
             const unsigned int sl[4] = {(unsigned int)v.x, (unsigned int)v.y, (unsigned int)v.z, (unsigned int)v.w};
-            const unsigned int rr[4] = {rk.x, rk.y, rk.z, rk.w};
+            bool in[4], any = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                in[i] = sl[i] - slot_lo < span;
+                any |= in[i];
+            }
+            if (!any && !node_out) continue;
             uint2 inf[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) inf[i] = nv.info[sl[i]];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) raw[(size_t)inf[i].y + rr[i]] = (uint32_t)(r_lo + jr[i] + read_base);
-            __stcs(reinterpret_cast<int4 *>(win_node + w), make_int4((int)inf[0].x, (int)inf[1].x, (int)inf[2].x, (int)inf[3].x));
+            for (int i = 0; i < 4; ++i) inf[i] = (in[i] || node_out) ? nv.info[sl[i]] : make_uint2(0u, 0u);
+            if (any) {
+                const uint4 rk = __ldcs(reinterpret_cast<const uint4 *>(win_rank + w));
+                const int4 rd = __ldcs(reinterpret_cast<const int4 *>(win_read + w));
+                if (in[0]) raw[(size_t)inf[0].y + rk.x] = (uint32_t)rd.x;
+                if (in[1]) raw[(size_t)inf[1].y + rk.y] = (uint32_t)rd.y;
+                if (in[2]) raw[(size_t)inf[2].y + rk.z] = (uint32_t)rd.z;
+                if (in[3]) raw[(size_t)inf[3].y + rk.w] = (uint32_t)rd.w;
+            }
+            if (node_out)
+                __stcs(reinterpret_cast<int4 *>(node_out + w), make_int4((int)inf[0].x, (int)inf[1].x, (int)inf[2].x, (int)inf[3].x));
         } else {
             for (int i = 0; i < 4 && w + i < W; ++i) {
-                const uint2 inf = nv.info[(unsigned int)win_node[w + i]];
-                win_node[w + i] = (int)inf.x;
-                raw[(size_t)inf.y + win_rank[w + i]] = (uint32_t)(r_lo + sj[lane * 4 + i] + read_base);
+                const unsigned int sl = (unsigned int)win_slot[w + i];
+                const uint2 inf = nv.info[sl];
+                if (sl - slot_lo < span) raw[(size_t)inf.y + win_rank[w + i]] = (uint32_t)win_read[w + i];
+                if (node_out) node_out[w + i] = (int)inf.x;
             }
         }
-        __syncwarp();
     }
 }
 
@@ -575,42 +548,26 @@ __global__ void k_compact_edges(const int *__restrict__ keep, const int *__restr
 }
 
 // remove_node_from_reads (construct_graph.py:442-461): windows of removed nodes become None and
-// their reads join _readsToCorrect.  One warp per 128-window tile; the read of a window is looked up
-// only in tiles that lose a window.
-__global__ void __launch_bounds__(256) k_mask_windows(const int *__restrict__ node_keep, const int *__restrict__ node_newidx,
-                                                      int32_t *__restrict__ win_node, int8_t *__restrict__ win_dir,
-                                                      const int64_t *__restrict__ win_off,
-                                                      const int32_t *__restrict__ wtile_r0, const long long R,
-                                                      int32_t *__restrict__ win_start, int32_t *__restrict__ win_end,
-                                                      const long long W, uint8_t *__restrict__ to_correct) {
-    __shared__ __align__(16) int s_j[8][WT];
-    const int lane = threadIdx.x & 31;
-    int *sj = s_j[threadIdx.x >> 5];
-    const long long n_wtiles = (W + WT - 1) / WT;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long tile = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; tile < n_wtiles; tile += n_warps) {
-        unsigned int gone = 0;  // bit i: window w0 + lane * 4 + i was removed now
-        const long long w = tile * WT + lane * 4;
-        for (int i = 0; i < 4 && w + i < W; ++i) {
-            const int n = win_node[w + i];
-            if (n < 0) continue;
-            if (node_keep[n]) {
-                win_node[w + i] = node_newidx[n];
-            } else {
-                win_node[w + i] = -1;
-                win_dir[w + i] = 0;
-                if (win_start) {
-                    win_start[w + i] = -1;
-                    win_end[w + i] = -1;
-                }
-                gone |= 1u << i;
+// their reads join _readsToCorrect
+__global__ void k_mask_windows(const int *__restrict__ node_keep, const int *__restrict__ node_newidx,
+                               int32_t *__restrict__ win_node, int8_t *__restrict__ win_dir,
+                               const int32_t *__restrict__ win_read, const int32_t read_base,
+                               int32_t *__restrict__ win_start, int32_t *__restrict__ win_end, const long long W,
+                               uint8_t *__restrict__ to_correct) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += stride) {
+        const int n = win_node[w];
+        if (n < 0) continue;
+        if (node_keep[n]) {
+            win_node[w] = node_newidx[n];
+        } else {
+            win_node[w] = -1;
+            win_dir[w] = 0;
+            if (win_start) {
+                win_start[w] = -1;
+                win_end[w] = -1;
             }
-        }
-        if (__any_sync(0xffffffffu, gone != 0)) {
-            const int r_lo = tile_reads(win_off, wtile_r0, tile, n_wtiles, R, sj, lane);
-            for (int i = 0; i < 4; ++i)
-                if (gone & (1u << i)) to_correct[r_lo + sj[lane * 4 + i]] = 1;
-            __syncwarp();
+            to_correct[win_read[w] - read_base] = 1;
         }
     }
 }

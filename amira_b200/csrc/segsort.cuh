@@ -11,13 +11,14 @@
 // Segment sizes span five orders of magnitude (coverage-1 error nodes .. nodes on every read), so:
 //   n <= 1          copy
 //   n <= 8          one THREAD: 19-comparator network in registers (32 consecutive segments per warp)
-//   n <= 256        one WARP: bitonic network, 1..8 keys per lane in registers, shuffles for the
+//   n <= 256        one WARP, inline: bitonic network, 1..8 keys per lane in registers, shuffles for the
 //                   lane-crossing stages
-//   n <= 4096       one WARP: LSD radix sort, `match.any` ranking, per-warp digit counters in shared memory
-//   larger          one CTA: the same radix sort, 8 warps on contiguous chunks (any size)
-// The radix passes ping-pong between two global buffers A and B (segments are a few KB: the traffic stays
-// in L2).  Source and destination may differ (out of place: the source segments may even be laid out in a
-// different order, `a_start`), which decides the parity of the pass count: the last pass must land in the
+//   n <= 4096       one WARP, from a work list (k_segsort_warp): bucket sort -- the keys are dealt into ~n/4
+//                   equal-width value buckets, every lane sorts whole buckets with the 8-key network
+//   larger          one CTA (k_segsort_radix): LSD radix sort, 8 warps on contiguous chunks, `match.any`
+//                   ranking, ping-pong between the two global buffers A and B (any size)
+// Source and destination may differ (out of place: the source segments may even be laid out in a different
+// order, `a_start`), which decides the parity of the radix pass count: the last pass must land in the
 // destination.  Values are < 0xFFFFFFFF (read / edge indices are < 2^31); 0xFFFFFFFF pads.
 #pragma once
 
@@ -26,7 +27,8 @@
 namespace amira {
 
 constexpr int SEG_BITONIC_MAX = 256;
-constexpr int SEG_WARP_MAX = 4096;
+constexpr int SEG_WARP_MAX = 4096;   // largest segment one warp bucket-sorts
+constexpr int SEG_STAGE_MAX = 8192;  // largest segment the radix kernel stages in shared memory
 constexpr int SEG_RADIX_THREADS = 256;
 constexpr int SEG_RADIX_WARPS = SEG_RADIX_THREADS / 32;
 constexpr int SEG_MAX_DIGIT_BITS = 11;
@@ -194,6 +196,125 @@ __global__ void __launch_bounds__(256) k_segsort_main(const SegJob J, const SegW
     }
 }
 
+// Segments of 257 .. SEG_WARP_MAX keys from the first work list, one warp each: BUCKET sort.  A node's reads are
+// spread evenly over its value range, so the keys are dealt (shared-memory counters, two passes) into
+// K ~ n/4 equal-width value buckets of ~2-4 keys, and every lane then sorts whole buckets on its own with the
+// 8-key register network: ~2 warp instructions per key, against ~20 for a bitonic network over the whole
+// segment (measured: 330M warp instructions, 0.7 ms for the 16M keys of this class on the C5 shard).  Buckets
+// above 8 keys (a few per cent) go through the warp networks; a segment so skewed that a bucket exceeds 256 keys
+// is handed to the radix kernel.
+constexpr int SEG_BUCKETS = 1024;
+__global__ void __launch_bounds__(128) k_segsort_warp(const SegJob J, const SegWork work) {
+    __shared__ unsigned int s_cnt[4][SEG_BUCKETS + 32];
+    const int lane = threadIdx.x & 31;
+    unsigned int *c = s_cnt[threadIdx.x >> 5];
+    const bool dst_is_b = (J.passes & 1) != 0;
+    const long long n_mid = min((long long)work.counters[0], work.cap);
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long my_dups = 0;
+    for (long long w = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; w < n_mid; w += n_warps) {
+        const long long s = work.list[w];
+        const long long o = J.off[s];
+        const int n = (int)(J.off[s + 1] - o);
+        const uint32_t *const ga = J.a + (J.a_start ? (long long)J.a_start[s] : o);
+        uint32_t *const gb = J.b + o;
+        uint32_t *const dst = dst_is_b ? gb : J.a + o;  // in place: a_start is null, the source is the destination
+        // value range of the segment
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t x = ga[i];
+            mn = min(mn, x);
+            mx = max(mx, x);
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        // K = 2^lgK buckets with n/4 <= K < n/2 (at most SEG_BUCKETS); bucket(x) = (x - mn) >> shift with the smallest
+        // shift that stays below K
+        int lgK = 6;
+        while ((4 << lgK) < n && (1 << lgK) < SEG_BUCKETS) ++lgK;
+        const int K = 1 << lgK;
+        int shift = 0;
+        while (((mx - mn) >> shift) >= (uint32_t)K) ++shift;
+        for (int i = lane; i <= K; i += 32) c[i] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) atomicAdd(&c[1 + ((ga[i] - mn) >> shift)], 1u);
+        __syncwarp();
+        // inclusive scan of c[0..K]: c[b] becomes the start of bucket b (c[0] = 0); each lane owns K/32 consecutive
+        // counters (+ the last lane the extra one)
+        unsigned int biggest = 0;
+        {
+            const int per = K >> 5;
+            unsigned int sum = 0;
+            for (int i = 0; i < per; ++i) {
+                const unsigned int v = c[1 + lane * per + i];
+                biggest = max(biggest, v);
+                sum += v;
+            }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, dd);
+                if (lane >= dd) incl += t;
+            }
+            unsigned int run = incl - sum;
+            for (int i = 0; i < per; ++i) {
+                run += c[1 + lane * per + i];
+                c[1 + lane * per + i] = run;
+            }
+        }
+        if (__any_sync(0xffffffffu, biggest > 256u)) {
+            if (lane == 0) {
+                const unsigned int pos = atomicAdd(&work.counters[1], 1u);
+                if ((long long)pos < work.cap) work.list[work.cap - 1 - pos] = s;
+            }
+            continue;
+        }
+        __syncwarp();
+        // deal the keys: the running start of bucket b is c[b]; afterwards c[b] is the END of bucket b
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t x = ga[i];
+            gb[atomicAdd(&c[(x - mn) >> shift], 1u)] = x;
+        }
+        __syncwarp();
+        unsigned int d = 0;
+        for (int b0 = 0; b0 < K; b0 += 32) {
+            const int b = b0 + lane;
+            const int start = b ? (int)c[b - 1] : 0;
+            const int m = (int)c[b] - start;
+            if (m >= 1 && m <= 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = i < m ? gb[start + i] : SEG_PAD;
+                sort8(v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < m) {
+                        dst[start + i] = v[i];
+                        if (i > 0 && v[i] == v[i - 1]) ++d;
+                    }
+            }
+            unsigned int big = __ballot_sync(0xffffffffu, m > 8);
+            while (big) {
+                const int l = __ffs(big) - 1;
+                big &= big - 1;
+                const int bs = __shfl_sync(0xffffffffu, start, l), bm = __shfl_sync(0xffffffffu, m, l);
+                unsigned int sd;
+                if (bm <= 32) sd = warp_sort_segment<1>(gb + bs, dst + bs, bm, lane);
+                else if (bm <= 64) sd = warp_sort_segment<2>(gb + bs, dst + bs, bm, lane);
+                else if (bm <= 128) sd = warp_sort_segment<4>(gb + bs, dst + bs, bm, lane);
+                else sd = warp_sort_segment<8>(gb + bs, dst + bs, bm, lane);
+                if (lane == 0) d += sd;
+            }
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) d += __shfl_xor_sync(0xffffffffu, d, dd);
+        if (J.dups && lane == 0) J.dups[s] = d;
+        if (lane == 0) my_dups += d;
+        __syncwarp();
+    }
+    if (J.total_dups && lane == 0 && my_dups) atomicAdd(J.total_dups, my_dups);
+}
+
 // ---- LSD radix sort ----------------------------------------------------------------------------------
 // One pass of one warp over keys src[0 .. n) (in order): stable scatter into dst by digit, with the
 // warp's running digit offsets in cnt[] (shared memory; on entry the exclusive start of every digit).
@@ -239,77 +360,41 @@ __device__ __forceinline__ unsigned int count_dups(const uint32_t *__restrict__ 
     return d;
 }
 
-__global__ void __launch_bounds__(SEG_RADIX_THREADS) k_segsort_radix(const SegJob J, const SegWork work) {
-    extern __shared__ unsigned int s_cnt[];  // [SEG_RADIX_WARPS][1 << digit_bits]
+// Shared memory: [SEG_RADIX_WARPS][D] digit counters, then two key buffers of kcap keys each (kcap may be 0).
+// A segment of n <= kcap keys is staged there and its passes run at shared-memory latency; larger segments
+// ping-pong between the two global buffers.
+__global__ void __launch_bounds__(SEG_RADIX_THREADS) k_segsort_radix(const SegJob J, const SegWork work, const int kcap) {
+    extern __shared__ unsigned int s_mem[];
     __shared__ unsigned int s_warp[SEG_RADIX_WARPS];
     __shared__ unsigned int s_dup;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = 1 << J.digit_bits;
     const uint32_t mask = (uint32_t)D - 1u;
+    unsigned int *s_cnt = s_mem;
     unsigned int *cnt = s_cnt + warp * D;
+    uint32_t *kb0 = s_mem + SEG_RADIX_WARPS * D, *kb1 = kb0 + kcap;
+    uint32_t *const final_base = (J.passes & 1) ? J.b : J.a;
     const long long n_mid = min((long long)work.counters[0], work.cap);
     const long long n_big = min((long long)work.counters[1], work.cap - n_mid);
-
-    // ---- warp-sized segments: one warp each
-    const long long n_warps = (long long)gridDim.x * SEG_RADIX_WARPS;
-    for (long long w = (long long)blockIdx.x * SEG_RADIX_WARPS + warp; w < n_mid; w += n_warps) {
-        const long long s = work.list[w];
-        const long long o = J.off[s], n = J.off[s + 1] - o;
-        uint32_t *buf[2] = {J.a + (J.a_start ? (long long)J.a_start[s] : o), J.b + o};
-        for (int pass = 0; pass < J.passes; ++pass) {
-            const uint32_t *src = buf[pass & 1];
-            uint32_t *dst = buf[(pass & 1) ^ 1];
-            const int shift = pass * J.digit_bits;
-            for (int i = lane; i < D; i += 32) cnt[i] = 0;
-            __syncwarp();
-            radix_count(src, 0, n, shift, mask, cnt, lane);
-            // exclusive scan of the D counters: each lane owns D/32 consecutive ones
-            {
-                const int per = D >> 5;  // D >= 32
-                unsigned int sum = 0;
-                for (int i = 0; i < per; ++i) sum += cnt[lane * per + i];
-                unsigned int incl = sum;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, dd);
-                    if (lane >= dd) incl += t;
-                }
-                unsigned int run = incl - sum;
-                for (int i = 0; i < per; ++i) {
-                    const unsigned int c = cnt[lane * per + i];
-                    cnt[lane * per + i] = run;
-                    run += c;
-                }
-            }
-            __syncwarp();
-            radix_scatter(src, dst, 0, n, shift, mask, cnt, lane);
-        }
-        if (J.dups) {
-            unsigned int d = count_dups(buf[J.passes & 1], 0, n, lane, 32);
-#pragma unroll
-            for (int dd = 16; dd > 0; dd >>= 1) d += __shfl_xor_sync(0xffffffffu, d, dd);
-            if (lane == 0) {
-                J.dups[s] = d;
-                if (d && J.total_dups) atomicAdd(J.total_dups, (unsigned long long)d);
-            }
-        }
-    }
-    __syncthreads();
 
     // ---- larger segments: the whole CTA, warp w on the w-th contiguous chunk
     for (long long w = blockIdx.x; w < n_big; w += gridDim.x) {
         const long long s = work.list[work.cap - 1 - w];
         const long long o = J.off[s], n = J.off[s + 1] - o;
-        uint32_t *buf[2] = {J.a + (J.a_start ? (long long)J.a_start[s] : o), J.b + o};
+        uint32_t *ga = J.a + (J.a_start ? (long long)J.a_start[s] : o), *gb = J.b + o;
+        const bool staged = n <= kcap;
+        uint32_t *x = staged ? kb0 : ga, *y = staged ? kb1 : gb;
+        if (staged) {
+            for (long long i = threadIdx.x; i < n; i += SEG_RADIX_THREADS) x[i] = ga[i];
+            __syncthreads();
+        }
         const long long chunk = ((n + SEG_RADIX_WARPS - 1) / SEG_RADIX_WARPS + 31) & ~31ll;
         const long long lo = min(n, warp * chunk), hi = min(n, lo + chunk);
         for (int pass = 0; pass < J.passes; ++pass) {
-            const uint32_t *src = buf[pass & 1];
-            uint32_t *dst = buf[(pass & 1) ^ 1];
             const int shift = pass * J.digit_bits;
             for (int i = lane; i < D; i += 32) cnt[i] = 0;
             __syncwarp();
-            radix_count(src, lo, hi, shift, mask, cnt, lane);
+            radix_count(x, lo, hi, shift, mask, cnt, lane);
             __syncthreads();
             // digit d, warp w starts at (keys with smaller digits) + (keys with digit d in earlier warps):
             // thread t owns the digits t * per .. + per - 1
@@ -339,13 +424,27 @@ __global__ void __launch_bounds__(SEG_RADIX_THREADS) k_segsort_radix(const SegJo
                         }
             }
             __syncthreads();
-            radix_scatter(src, dst, lo, hi, shift, mask, cnt, lane);
+            radix_scatter(x, y, lo, hi, shift, mask, cnt, lane);
             __syncthreads();
+            uint32_t *t = x;
+            x = y;
+            y = t;
+        }
+        // x holds the sorted keys
+        if (threadIdx.x == 0) s_dup = 0;
+        __syncthreads();
+        unsigned int d = 0;
+        if (staged) {
+            uint32_t *dst = final_base + o;
+            for (long long i = threadIdx.x; i < n; i += SEG_RADIX_THREADS) {
+                const uint32_t v = x[i];
+                dst[i] = v;
+                if (i > 0 && x[i - 1] == v) ++d;
+            }
+        } else if (J.dups) {
+            d = count_dups(x, 0, n, threadIdx.x, SEG_RADIX_THREADS);
         }
         if (J.dups) {
-            if (threadIdx.x == 0) s_dup = 0;
-            __syncthreads();
-            const unsigned int d = count_dups(buf[J.passes & 1], 0, n, threadIdx.x, SEG_RADIX_THREADS);
             if (d) atomicAdd(&s_dup, d);
             __syncthreads();
             if (threadIdx.x == 0) {

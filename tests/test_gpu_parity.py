@@ -346,3 +346,33 @@ def test_gpu_key_width_boundary_values(dg):
             ids[::12] = 1                                    # no palindromes at even k, some structure
             dg.build(ids, off, k)
             assert O.diff_arrays(dg.arrays(), c_oracle.COracleGraph(ids, off, k).arrays()) == [], (k, vals)
+
+
+def test_gpu_repeated_resident_builds_replay_a_graph(dg):
+    """the same device-resident CSR built again and again (the k sweep / rebuild loop): from the second repeat on the
+    library replays a captured CUDA graph -- results must stay those of the oracle, also when k or the reads change
+    in between and when a replayed build is followed by filters"""
+    import torch
+    from amira_b200 import synth
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    ids, off = synth.generate(synth.CONFIGS["c2"], 0, 8000)
+    ids2, off2 = synth.generate(synth.CONFIGS["c3"], 0, 6000)
+    d = [torch.from_numpy(x).cuda() for x in (ids, off, ids2, off2)]
+    torch.cuda.synchronize()
+    ref = {3: c_oracle.COracleGraph(ids, off, 3).arrays(), 5: c_oracle.COracleGraph(ids, off, 5).arrays()}
+    ref2 = c_oracle.COracleGraph(ids2, off2, 3)
+    for k in (3, 3, 3, 3, 5, 5, 5, 3, 3, 3):
+        dg.build(d[0], d[1], k, on_device=True, wait=False)
+        assert O.diff_arrays(dg.arrays(), ref[k]) == [], k
+    for rep in range(4):
+        dg.build(d[2], d[3], 3, on_device=True, wait=False)
+    assert O.diff_arrays(dg.arrays(), ref2.arrays()) == []
+    ref2.remove_low_coverage_components(5)
+    dg.remove_low_coverage_components(5)
+    ref2.filter_graph(3, 1)
+    dg.filter_graph(3, 1)
+    assert O.diff_arrays(dg.arrays(), ref2.arrays()) == []
+    for rep in range(3):                      # back-to-back replays without looking at the results in between
+        dg.build(d[0], d[1], 3, on_device=True, wait=False)
+    assert O.diff_arrays(dg.arrays(), ref[3]) == []
