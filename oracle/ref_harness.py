@@ -1,7 +1,9 @@
-"""Import the UNMODIFIED upstream Amira package from the read-only checkout -- TEST INFRASTRUCTURE ONLY.
+"""Import the UNMODIFIED upstream Amira package -- TEST INFRASTRUCTURE ONLY.
 
-Only usable in the build container (``/root/reference`` does not exist on the GPU box);
-used by ``oracle/make_golden.py`` to generate ``tests/golden/`` and by nothing at run time.
+From the read-only checkout (``/root/reference``, build container) or, where that does not exist (the GPU box),
+from ``baseline/_ref/`` -- the git-ignored ``pip install --target`` copy made by ``baseline/install_ref.py`` that
+travels with the repository snapshot.  Used by ``oracle/make_golden.py`` to generate ``tests/golden/`` and by
+``bench.py`` to time upstream's own ``GeneMerGraph(readDict, k)`` on the host cores beside the GPU numbers.
 
 ``amira/construct_graph.py:9,11,19`` imports ``sourmash``, ``suffix_tree`` and (through
 ``graph_utils``) ``matplotlib``/``pysam`` at module import; none is called on the graph-build
@@ -15,7 +17,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("AMIRA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("AMIRA_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "amira", "construct_graph.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
