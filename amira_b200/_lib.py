@@ -20,6 +20,8 @@ EXPORTED = (
     "amira_gmg_build", "amira_gmg_sync", "amira_gmg_sizes", "amira_gmg_export_nodes", "amira_gmg_export_edges",
     "amira_gmg_export_reads", "amira_gmg_remove_low_coverage_components", "amira_gmg_filter",
     "amira_gmg_filter_mask_sizes", "amira_gmg_export_filter_masks", "amira_gmg_nccl_unique_id", "amira_gmg_comm_init", "amira_gmg_atomic_peak", "amira_gmg_debug_layout", "amira_gmg_debug_segsort",
+    "amira_gmg_read_length_coverages", "amira_gmg_node_coverage_stats", "amira_gmg_junk_read_mask", "amira_gmg_nodes_containing",
+    "amira_gmg_remove_nodes", "amira_gmg_remove_nodes_without_reads_of", "amira_gmg_linear_steps",
 )
 
 _lib = None
@@ -63,6 +65,13 @@ def load():
     lib.amira_gmg_export_filter_masks.argtypes = [vp, vp, vp]
     lib.amira_gmg_nccl_unique_id.argtypes = [vp]
     lib.amira_gmg_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.amira_gmg_read_length_coverages.argtypes = [vp, vp, i32, vp]
+    lib.amira_gmg_node_coverage_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(u32)]
+    lib.amira_gmg_junk_read_mask.argtypes = [vp, C.c_double, vp]
+    lib.amira_gmg_nodes_containing.argtypes = [vp, vp, i32, vp]
+    lib.amira_gmg_remove_nodes.argtypes = [vp, vp]
+    lib.amira_gmg_remove_nodes_without_reads_of.argtypes = [vp, vp, i32]
+    lib.amira_gmg_linear_steps.argtypes = [vp] * 8
     lib.amira_gmg_debug_layout.argtypes = [vp, C.c_int]
     lib.amira_gmg_debug_segsort.argtypes = [vp, vp, vp, i64, vp, C.POINTER(i64), C.c_int, i64]
     lib.amira_gmg_atomic_peak.argtypes = [vp, i64, i64] + [C.POINTER(C.c_double)] * 3

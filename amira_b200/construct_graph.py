@@ -9,6 +9,11 @@ exported arrays into the dictionaries and ``Node`` / ``Edge`` objects downstream
 ``_readsToCorrect``.  The single-object accessors and mutators of the same surface
 (``add_node``, ``remove_node``, ...) are plain host code over those objects, as upstream's are.
 
+The host objects are materialised LAZILY: the constructor only encodes the reads and enqueues the device
+build; the dictionaries and ``Node`` / ``Edge`` objects are created the first time something reaches for
+``_nodes`` / ``_edges`` / the per-read lists.  Filters, component removal, the coverage statistics, the junk-read
+and valid-read selections and the GML writer work on the device arrays and never need them.
+
 There is no CPU build: without ``libamira_gmg.so`` or without a CUDA device construction fails.
 
 To run upstream's own correction / path-finding methods on top of the GPU build, see
@@ -19,6 +24,7 @@ from __future__ import annotations
 import os
 import statistics
 import weakref
+import zlib
 
 import numpy as np
 
@@ -69,14 +75,39 @@ class _Classes:
         return e
 
 
+_LAZY_ATTRS = ("_nodes", "_edges", "_readNodes", "_readNodeDirections", "_readNodePositions", "_shortReads",
+               "_readsToCorrect")
+
+
+def _lazy_property(name):
+    slot = "_m" + name
+
+    def get(self):
+        if self.__dict__.get("_lazy"):
+            self._materialise_now()
+        return self.__dict__[slot]
+
+    def set_(self, value):
+        self.__dict__[slot] = value
+
+    return property(get, set_)
+
+
 class GeneMerGraph:
     _cls = _Classes
+    for _a in _LAZY_ATTRS:
+        locals()[_a] = _lazy_property(_a)
+    del _a
 
     def __init__(self, readDict, kmerSize, gene_positions=None, device=None):
         # an encode.EncodedReads in place of the dict: the strings were parsed once, reuse the CSR
+        self._lazy = False
         self._encoded = readDict if isinstance(readDict, encode.EncodedReads) else None
         if self._encoded is not None:
-            gene_positions = self._encoded.positions if gene_positions is None else gene_positions
+            if gene_positions is not None and gene_positions is not self._encoded.positions:
+                # explicit positions win: encode them against the same reads (the cached CSR has none / others)
+                self._encoded = encode.EncodedReads(self._encoded.reads, gene_positions)
+            gene_positions = self._encoded.positions
             readDict = self._encoded.reads
         self._reads = readDict
         self._kmerSize = kmerSize
@@ -94,8 +125,11 @@ class GeneMerGraph:
         self._device_synced = False      # device state == host objects
         self._node_order = []            # node hashes in device index order
         self._edge_order = []
+        self._node_objs = []             # Node objects in device index order
         self._read_ids = []
         self._win_off = None
+        self._device_ops = ()
+        self._steps_cache = None
         self.timings = {}
         _lib.load()                      # fail loudly if the CUDA library is missing
         if len(readDict) > 0:
@@ -115,18 +149,32 @@ class GeneMerGraph:
     def _build_on_device(self):
         vocab, ids, off, ps, pe = self._encode()
         self._vocab = vocab
+        self._csr_fingerprint = (len(ids), int(off[-1]) if len(off) else 0, zlib.crc32(np.ascontiguousarray(ids).tobytes()))
+        self._read_len = np.diff(off)
         h = _handle(self._device)
         h.owner = None
         if self._encoded is not None and hasattr(h, "build_resident"):
             h.build_resident(self._encoded, int(self._kmerSize), self._device)
         else:
             h.build(ids, off, int(self._kmerSize), ps, pe)
-        arrays = h.arrays()
         h.owner = weakref.ref(self)
-        self._materialise(arrays, vocab)
-        # kept for array-level statistics (graph_utils.get_overall_mean_node_coverages)
-        self._incidence_arrays = (arrays["node_reads"], np.diff(off), len(arrays["node_cov"]))
+        self._read_ids = list(self._reads)
         self._device_synced = True
+        self._lazy = True                # host objects on first use (_materialise_now)
+
+    def _materialise_now(self):
+        """create the host dictionaries and objects from the device arrays (first access to _nodes / _edges / ...)"""
+        if not self.__dict__.get("_lazy"):
+            return
+        self._lazy = False
+        h = self._require_device_state()
+        self._materialise(h.arrays(), self._vocab)
+
+    def _arrays(self, *fields):
+        """current device arrays of this graph (no host objects involved)"""
+        h = self._require_device_state()
+        a = h.arrays()
+        return a if not fields else tuple(a[f] for f in fields)
 
     def _materialise(self, a, vocab):
         C = self._cls
@@ -161,6 +209,7 @@ class GeneMerGraph:
             nodes[nh] = node
             node_objs.append(node)
         self._node_order = node_hashes
+        self._node_objs = node_objs
         # edges
         src, tgt = a["edge_src"].tolist(), a["edge_tgt"].tolist()
         sd, td, ecov = a["edge_sd"].tolist(), a["edge_td"].tolist(), a["edge_cov"].tolist()
@@ -178,19 +227,27 @@ class GeneMerGraph:
             for i, node in enumerate(node_objs):
                 node.forwardEdgeHashes = fw[fo[i]:fo[i + 1]]
                 node.backwardEdgeHashes = bw[bo[i]:bo[i + 1]]
-        # per-read lists
+        # per-read lists (windows of removed nodes are None: the arrays may come from a filtered device graph)
         woff = a["win_off"].tolist()
         self._win_off = woff
+        win = a["win_node"]
+        gone = win < 0
+        any_gone = bool(gone.any())
         if n_nodes:
-            nh_arr = np.empty(n_nodes, object)
-            nh_arr[:] = node_hashes
-            wn = nh_arr[a["win_node"]].tolist()
+            nh_arr = np.empty(n_nodes + 1, object)
+            nh_arr[:n_nodes] = node_hashes
+            nh_arr[n_nodes] = None
+            wn = nh_arr[np.where(gone, n_nodes, win)].tolist()
         else:
-            wn = []
+            wn = [None] * len(win)
         wd = a["win_dir"].tolist()
+        if any_gone:
+            wd = [None if g else d for d, g in zip(wd, gone.tolist())]
         has_pos = bool(self._genePositions)
         if has_pos:
             wp = list(zip(a["win_start"].tolist(), a["win_end"].tolist()))
+            if any_gone:
+                wp = [None if g else p for p, g in zip(wp, gone.tolist())]
         short = a["is_short"].tolist()
         rn, rd, rp = self._readNodes, self._readNodeDirections, self._readNodePositions
         for i, rid in enumerate(read_ids):
@@ -204,6 +261,7 @@ class GeneMerGraph:
                 rp[rid] = wp[lo:hi]
             else:
                 rp[rid] = [None] * (hi - lo)
+        self._readsToCorrect.update(rid for rid, c in zip(read_ids, a["to_correct"].tolist()) if c)
 
     def _require_device_state(self):
         """the device copy of this graph, rebuilt if another graph has used the handle since"""
@@ -214,7 +272,8 @@ class GeneMerGraph:
         h = _handle(self._device)
         if h.owner is None or h.owner() is not self:
             vocab, ids, off, ps, pe = self._encode()
-            if vocab.names != self._vocab.names:
+            fp = (len(ids), int(off[-1]) if len(off) else 0, zlib.crc32(np.ascontiguousarray(ids).tobytes()))
+            if vocab.names != self._vocab.names or fp != self._csr_fingerprint:
                 raise RuntimeError("the read dict of this graph changed since it was built; rebuild it first")
             h.owner = None
             h.build(ids, off, int(self._kmerSize), ps, pe)
@@ -223,10 +282,11 @@ class GeneMerGraph:
             h.owner = weakref.ref(self)
         return h
 
-    _device_ops: tuple = ()
-
     def _apply_device_removal(self, h):
         """mirror the device's last removal on the host objects (same deletions upstream performs)"""
+        self._steps_cache = None
+        if self.__dict__.get("_lazy"):
+            return                       # nothing materialised yet: the arrays are the graph
         node_keep, edge_keep = h.filter_masks()
         if node_keep.all() and edge_keep.all():
             return
@@ -246,6 +306,7 @@ class GeneMerGraph:
             node = nodes.pop(self._node_order[i])
             affected.update(node.get_list_of_reads())
         self._node_order = [nh for nh, kp in zip(self._node_order, node_keep.tolist()) if kp]
+        self._node_objs = [n for n, kp in zip(self._node_objs, node_keep.tolist()) if kp]
         # per-read lists: windows of removed nodes become None (remove_node_from_reads, :442-461)
         a = h.arrays_reads_only()
         wn = a["win_node"]
@@ -265,7 +326,7 @@ class GeneMerGraph:
         """upstream construct_graph.py:523-540"""
         minNodeCoverage = self.set_minNodeCoverage(minNodeCoverage)
         minEdgeCoverage = self.set_minEdgeCoverage(minEdgeCoverage)
-        if not self._nodes:
+        if self.get_total_number_of_nodes() == 0:
             return self
         h = self._require_device_state()
         h.filter_graph(max(int(minNodeCoverage), 0), max(int(minEdgeCoverage), 0))
@@ -275,7 +336,7 @@ class GeneMerGraph:
 
     def remove_low_coverage_components(self, min_component_coverage):
         """upstream construct_graph.py:950-958"""
-        if not self._nodes:
+        if self.get_total_number_of_nodes() == 0:
             return
         h = self._require_device_state()
         h.remove_low_coverage_components(max(int(min_component_coverage), 0))
@@ -349,13 +410,187 @@ class GeneMerGraph:
         assert not (geneOfInterest[0] == "+" or geneOfInterest[0] == "-"), \
             "Strand information cannot be present for any specified genes"
         assert isinstance(geneOfInterest, str), "Gene of interest is the wrong type"
+        if self._on_device():
+            nodes = self._nodes                                   # materialises; keeps _node_objs in device order
+            rank = self._gene_ranks([geneOfInterest])
+            if not rank:
+                return []
+            flags = self._require_device_state().nodes_containing(rank)
+            return [self._node_objs[i] for i in np.flatnonzero(flags).tolist()]
         return [n for n in self._nodes.values()
                 if geneOfInterest in [g.get_name() for g in n.get_canonical_geneMer()]]
 
+    def _gene_ranks(self, names) -> list:
+        """SHA ranks (1..V) of the gene names that occur in this graph's vocabulary"""
+        if getattr(self, "_rank_of", None) is None:
+            self._rank_of = {n: i + 1 for i, n in enumerate(self._vocab.names)}
+        return [self._rank_of[n] for n in names if n in self._rank_of]
+
+    def get_AMR_nodes(self, listOfGenes):
+        """upstream construct_graph.py:963-972: {node hash: node} of the nodes that contain any of the genes"""
+        if self._on_device():
+            nodes = self._nodes
+            h = self._require_device_state()
+            out = {}
+            for g in listOfGenes:                  # upstream's dict order: by gene, then by node
+                for r in self._gene_ranks([g]):
+                    for i in np.flatnonzero(h.nodes_containing([r])).tolist():
+                        out[self._node_order[i]] = self._node_objs[i]
+            return out
+        out = {}
+        for g in listOfGenes:
+            for node in self.get_nodes_containing(g):
+                out[node.__hash__()] = node
+        return out
+
+    def remove_non_AMR_associated_nodes(self, genesOfInterest):
+        """upstream construct_graph.py:2941-2959: drop every node that shares no read with a node holding one of the
+        genes.  On the device: flag nodes, mark their reads, keep the nodes that touch a marked read, compact."""
+        if self._on_device():
+            for g in genesOfInterest:
+                assert not (g[0] == "+" or g[0] == "-"), "Strand information cannot be present for any specified genes"
+            h = self._require_device_state()
+            ranks = self._gene_ranks(list(genesOfInterest))
+            h.remove_nodes_without_reads_of(ranks)
+            self._device_ops = self._device_ops + (("remove_nodes_without_reads_of", (tuple(ranks),)),)
+            self._apply_device_removal(h)
+            return
+        readsOfInterest = set()
+        for g in genesOfInterest:
+            for node in self.get_nodes_containing(g):
+                readsOfInterest.update(node.get_reads())
+        doomed = [n for n in self._nodes.values() if not readsOfInterest.intersection(n.get_list_of_reads())]
+        for node in doomed:
+            self.remove_node(node)
+
+    # ------------------------------------------------------------------ linear paths (upstream :722-861, 679-720)
+    def _linear_steps(self) -> dict:
+        """per node and side: upstream's one step of a linear-path walk (next node index, entry direction, extend flag)
+        and the node degrees -- from the device adjacency CSR (k_linear_steps), or from the host objects when the
+        graph was edited on the host since"""
+        if self._steps_cache is not None and self._on_device():
+            return self._steps_cache
+        nodes = self._nodes
+        if self._on_device():
+            st = {k: v.tolist() for k, v in self._require_device_state().linear_steps().items()}
+            st["index"] = {h: i for i, h in enumerate(self._node_order)}
+            st["hash"] = self._node_order
+            self._steps_cache = st
+            return st
+        order = list(nodes)
+        index = {h: i for i, h in enumerate(order)}
+        st = {"index": index, "hash": order, "degree": [self.get_degree(n) for n in nodes.values()]}
+        for side, getter in (("fw", "get_forward_edge_hashes"), ("bw", "get_backward_edge_hashes")):
+            nxt, dr, ext = [], [], []
+            for h, node in nodes.items():
+                eh = getattr(node, getter)()
+                take = len(eh) == 1 if side == "fw" else len(eh) > 0
+                if not take:
+                    nxt.append(-1); dr.append(0); ext.append(0)
+                    continue
+                e = self._edges[eh[0]]
+                t = e.get_targetNode()
+                nxt.append(index[t.__hash__()])
+                dr.append(e.get_targetNodeDirection())
+                ext.append(int(self.get_degree(t) in (1, 2) and t != node))
+            st[side + "_next"], st[side + "_dir"], st[side + "_ext"] = nxt, dr, ext
+        return st
+
+    def _walk(self, st, start: int, first_side: str, backward: bool, want_branched: bool) -> list:
+        """get_forward_path_from_node / get_backward_path_from_node on node indices"""
+        path = [start]
+        ext, nx, d = st[first_side + "_ext"][start], st[first_side + "_next"][start], st[first_side + "_dir"][start]
+        while ext:
+            if path[-1 if backward else 0] == nx:
+                break                                   # (upstream compares with the far end of the list and stops)
+            if backward:
+                path.insert(0, nx)
+            else:
+                path.append(nx)
+            side = ("bw" if d == -1 else "fw") if backward else ("fw" if d == 1 else "bw")
+            ext, nx, d = st[side + "_ext"][nx], st[side + "_next"][nx], st[side + "_dir"][nx]
+        if want_branched and nx is not None and nx >= 0:
+            if backward:
+                path.insert(0, nx)
+            else:
+                path.append(nx)
+        return path
+
+    def get_forward_path_from_node(self, node, startDirection, wantBranchedNode=False) -> list:
+        st = self._linear_steps()
+        i = st["index"][node.__hash__()]
+        return [st["hash"][j] for j in self._walk(st, i, "fw" if startDirection == 1 else "bw", False, wantBranchedNode)]
+
+    def get_backward_path_from_node(self, node, startDirection, wantBranchedNode=False) -> list:
+        st = self._linear_steps()
+        i = st["index"][node.__hash__()]
+        return [st["hash"][j] for j in self._walk(st, i, "bw" if startDirection == -1 else "fw", True, wantBranchedNode)]
+
+    def get_linear_path_for_node(self, node, wantBranchedNode=False) -> list:
+        """upstream construct_graph.py:849-861"""
+        d = node.get_geneMer().get_geneMerDirection()
+        back = self.get_backward_path_from_node(node, -1 * d, wantBranchedNode)
+        assert back[-1] == node.__hash__()
+        fwd = self.get_forward_path_from_node(node, d, wantBranchedNode)
+        assert fwd[0] == node.__hash__()
+        return back[:-1] + [node.__hash__()] + fwd[1:]
+
+    def remove_short_linear_paths(self, min_length, sample_genesOfInterest={}):
+        """upstream construct_graph.py:679-720: dead ends (degree-1 nodes) whose linear path is shorter than min_length
+        are removed unless the whole path is well covered, holds an AMR gene or is its whole component.  The paths
+        come from the device step table; the removal is one device pass (amira_gmg_remove_nodes)."""
+        st = self._linear_steps()
+        nodes = self._nodes
+        mean15 = self.get_mean_node_coverage() * 1.5 if len(nodes) else 0
+        paths_to_remove = {}
+        for i, node in enumerate(list(nodes.values())):
+            if st["degree"][st["index"][node.__hash__()]] != 1:
+                continue
+            path = self.get_linear_path_for_node(node)
+            if 0 < len(path) < min_length:
+                if all(nodes[n].get_node_coverage() > mean15 for n in path):
+                    continue
+                paths_to_remove.setdefault(node.get_component(), []).append(path)
+        AMR_nodes = self.get_AMR_nodes(sample_genesOfInterest)
+        removed = []
+        seen = set()
+        for component, paths in paths_to_remove.items():
+            in_comp = {n.__hash__() for n in self.get_nodes_in_component(component)} if component is not None else set()
+            for path in paths:
+                if component is not None and len(in_comp.intersection(path)) == len(in_comp):
+                    continue
+                for nh in path:
+                    if nh in AMR_nodes or nh in seen:
+                        continue
+                    seen.add(nh)
+                    removed.append(nh)
+        if not removed:
+            return []
+        if self._on_device():
+            h = self._require_device_state()
+            flags = np.zeros(len(self._node_order), np.uint8)
+            index = st["index"]
+            flags[[index[nh] for nh in removed]] = 1
+            h.remove_nodes(flags)
+            self._device_ops = self._device_ops + (("remove_nodes", (flags,)),)
+            self._apply_device_removal(h)
+        else:
+            for nh in removed:
+                self.remove_node(nodes[nh])
+        return removed
+
+    def _on_device(self) -> bool:
+        """the device copy still is this graph (no host-side mutation since the build / last device operation)"""
+        return bool(self._device_synced) and len(self._reads) > 0
+
     def get_total_number_of_nodes(self) -> int:
+        if self.__dict__.get("_lazy"):
+            return self._require_device_state().sizes_early()["nodes"]
         return len(self._nodes)
 
     def get_total_number_of_edges(self) -> int:
+        if self.__dict__.get("_lazy"):
+            return self._require_device_state().sizes_early()["edges"]
         return len(self._edges)
 
     def get_total_number_of_reads(self) -> int:
@@ -404,9 +639,17 @@ class GeneMerGraph:
 
     def remove_junk_reads(self, error_rate):
         """upstream construct_graph.py:1398-1420: reads with more than round(n * (1 - error_rate)) filtered
-        (None) nodes are rejected"""
+        (None) nodes are rejected.  On the device: one thread per read counts its None windows (k_junk_read_mask)."""
         reads, positions = self._reads, self._genePositions
         kept, kept_pos, rejected, rejected_pos = {}, {}, {}, {}
+        if self._on_device():
+            mask = self._require_device_state().junk_read_mask(error_rate).tolist()
+            for read_id, m in zip(self._read_ids, mask):
+                if m == 2:
+                    continue             # short read: not in _readNodes
+                (kept if m else rejected)[read_id] = reads[read_id]
+                (kept_pos if m else rejected_pos)[read_id] = positions[read_id]
+            return kept, kept_pos, rejected, rejected_pos
         for read_id, nodes in self._readNodes.items():
             ok = nodes.count(None) <= round(len(nodes) * (1 - error_rate))
             (kept if ok else rejected)[read_id] = reads[read_id]
@@ -415,18 +658,32 @@ class GeneMerGraph:
 
     def get_valid_reads_only(self):
         """upstream construct_graph.py:1422-1427"""
+        if self.__dict__.get("_lazy"):
+            to_correct = self._arrays("to_correct")[0].tolist()
+            return {r: self._reads[r] for r, bad in zip(self._read_ids, to_correct) if not bad}
         bad = self._readsToCorrect
         return {r: calls for r, calls in self._reads.items() if r not in bad}
 
     def get_all_node_coverages(self):
+        if self.__dict__.get("_lazy"):
+            return self._arrays("node_cov")[0].tolist()
         return [n.get_node_coverage() for n in self._nodes.values()]
 
     def get_mean_node_coverage(self):
+        """upstream construct_graph.py:868-871 (statistics.mean of the coverages: exact, int when it divides)"""
+        if self._on_device():
+            n = self.get_total_number_of_nodes()
+            if n == 0:
+                raise statistics.StatisticsError("mean requires at least one data point")
+            total, _ = self._require_device_state().node_coverage_stats()
+            return total // n if total % n == 0 else total / n
         return statistics.mean(self.get_all_node_coverages())
 
     # ------------------------------------------------------------------ single-object mutators (host)
     def _touch(self):
+        self._nodes                          # host edits need the host objects (materialise before going stale)
         self._device_synced = False
+        self._steps_cache = None
 
     def add_node_to_read(self, node, readId: str, node_direction: int, node_position=None):
         self._touch()
@@ -567,6 +824,8 @@ class GeneMerGraph:
         return [n for n in self._nodes.values() if n.get_component() == int(component)]
 
     def components(self) -> list:
+        if self.__dict__.get("_lazy"):
+            return sorted(set(self._arrays("node_comp")[0].tolist()))
         return sorted({n.get_component() for n in self._nodes.values()})
 
     def get_number_of_component(self) -> int:
@@ -610,7 +869,40 @@ class GeneMerGraph:
     def get_gene_mer_label(self, sourceNode) -> str:
         return "~~~".join(self.get_gene_mer_genes(sourceNode))
 
+    def _gml_from_arrays(self) -> list:
+        """the GML entries of upstream generate_gml (construct_graph.py:873-909) straight from the device arrays: node id =
+        insertion index, label from the canonical gene-mer, reads by id, edges in forward-then-backward list order"""
+        a = self._arrays()
+        names = self._vocab.names
+        signed = [None] * (2 * len(names) + 1)
+        V = len(names)
+        for r, n in enumerate(names, 1):
+            signed[V + r], signed[V - r] = "+" + n, "-" + n
+        key = (a["node_key"].astype(np.int64) + V).tolist()
+        cov, comp = a["node_cov"].tolist(), a["node_comp"].tolist()
+        roff, reads = a["node_reads_off"].tolist(), a["node_reads"].tolist()
+        fo, fe, bo, be = a["fw_off"].tolist(), a["fw_edges"].tolist(), a["bw_off"].tolist(), a["bw_edges"].tolist()
+        tgt, sd, td, ecov = a["edge_tgt"].tolist(), a["edge_sd"].tolist(), a["edge_td"].tolist(), a["edge_cov"].tolist()
+        rid = self._read_ids
+        out = ["graph\t[", "multigraph 1"]
+        for i in range(len(cov)):
+            out.append(self.write_node_entry(i, "~~~".join(signed[g] for g in key[i]), cov[i],
+                                             [rid[r] for r in reads[roff[i]:roff[i + 1]]], comp[i], None))
+            for e in fe[fo[i]:fo[i + 1]] + be[bo[i]:bo[i + 1]]:
+                if ecov[e] == 0:
+                    continue
+                out.append(self.write_edge_entry(i, tgt[e], sd[e], td[e], ecov[e]))
+        out.append("]")
+        return out
+
     def generate_gml(self, output_file: str, geneMerSize: int, min_node_coverage: int, min_edge_coverage: int):
+        if self.__dict__.get("_lazy") or (self._on_device() and not any(n.get_color() for n in self._node_objs)):
+            graph_data = self._gml_from_arrays()
+            if not self.__dict__.get("_lazy"):
+                self.assign_Id_to_nodes()
+            self.write_gml_to_file(".".join([output_file, str(geneMerSize), str(min_node_coverage), str(min_edge_coverage)]),
+                                   graph_data)
+            return graph_data
         graph_data = ["graph\t[", "multigraph 1"]
         self.assign_Id_to_nodes()
         for node in self._nodes.values():
@@ -682,18 +974,22 @@ def bind_upstream(upstream_construct_graph):
             return e
 
     ours = GeneMerGraph
-    gpu_methods = ("__init__", "_encode", "_build_on_device", "_materialise", "_require_device_state",
-                   "_apply_device_removal", "filter_graph", "remove_low_coverage_components", "_touch",
-                   "remove_junk_reads", "get_valid_reads_only")
+    gpu_methods = ("__init__", "_encode", "_build_on_device", "_materialise", "_materialise_now", "_arrays", "_on_device",
+                   "_require_device_state", "_apply_device_removal", "filter_graph", "remove_low_coverage_components",
+                   "_touch", "remove_junk_reads", "get_valid_reads_only", "get_total_number_of_nodes",
+                   "get_total_number_of_edges", "get_all_node_coverages", "get_mean_node_coverage", "components",
+                   "get_nodes_containing", "_gene_ranks", "get_AMR_nodes", "remove_non_AMR_associated_nodes", "_linear_steps",
+                   "_walk", "get_forward_path_from_node", "get_backward_path_from_node", "get_linear_path_for_node",
+                   "remove_short_linear_paths", "_gml_from_arrays", "generate_gml") + _LAZY_ATTRS
     ns = {name: ours.__dict__[name] for name in gpu_methods}
     ns["_cls"] = _Up
-    ns["_device_ops"] = ()
     # host mutators must mark the device copy stale
     for name in ("add_node", "add_node_to_read", "add_node_to_nodes", "add_edge_to_edges", "add_edge_to_node",
                  "remove_edge", "remove_edge_from_edges", "remove_node_from_reads"):
         base = getattr(up.GeneMerGraph, name)
 
         def wrapped(self, *a, _base=base, **kw):
+            self._nodes                      # host edits need the host objects
             self._device_synced = False
             return _base(self, *a, **kw)
 

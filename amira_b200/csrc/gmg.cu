@@ -9,6 +9,7 @@
 #include <cub/device/device_radix_sort.cuh>  // multi-GPU merge only (ordering of the merged records)
 
 #include "post_kernels.cuh"
+#include "stats.cuh"
 #include "sharded.cuh"
 
 namespace amira {
@@ -792,18 +793,16 @@ int finish(amira_gmg *h, bool early) {
     return h->last_status;
 }
 
-int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
+// everything a filter / node removal touches, reserved before its kernels are enqueued
+int filter_reserve(amira_gmg *h) {
     if (!h->built) {
         set_error("filter before build");
         return AMIRA_E_STATE;
     }
     AMIRA_TRY(finish(h, false));
-    const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
+    if (!h->built) return h->last_status;
+    const int64_t N = h->n_nodes, E = h->n_edges;
     const int k = h->k;
-    cudaStream_t st = h->stream;
-    h->filt_N = N;
-    h->filt_E = E;
-    if (N == 0) return AMIRA_OK;
     AMIRA_TRY(h->keep_n.reserve(sizeof(int) * 2 * (N + 2)));
     AMIRA_TRY(h->keep_e.reserve(sizeof(int) * 2 * (E + 2)));
     AMIRA_TRY(h->node_key2.reserve(sizeof(int32_t) * std::max<int64_t>(1, N * k)));
@@ -817,10 +816,23 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
     AMIRA_TRY(h->e_sd2.reserve(E + 2));
     AMIRA_TRY(h->e_td2.reserve(E + 2));
     AMIRA_TRY(h->e_cov2.reserve(sizeof(uint32_t) * (E + 2)));
-    if (mode == 1) AMIRA_TRY(h->comp_max.reserve(sizeof(uint32_t) * (h->n_comps + 2)));
+    AMIRA_TRY(h->comp_max.reserve(sizeof(uint32_t) * (h->n_comps + 2)));
     // the graph only shrinks: the capacities of the build (or of the previous filter) still hold
     h->cap_nodes = std::max<int64_t>(h->cap_nodes, N);
     h->cap_edges = std::max<int64_t>(h->cap_edges, E);
+    return AMIRA_OK;
+}
+
+// mode 0: filter_graph thresholds; mode 1: remove_low_coverage_components; mode 2: the keep flags of the nodes are
+// already in keep_n (remove_node for every node whose flag is 0)
+int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
+    AMIRA_TRY(filter_reserve(h));
+    const int64_t N = h->n_nodes, E = h->n_edges, W = h->W;
+    const int k = h->k;
+    cudaStream_t st = h->stream;
+    h->filt_N = N;
+    h->filt_E = E;
+    if (N == 0) return AMIRA_OK;
     Phase ph(h, AMIRA_PH_FILTER);
     int *keep_n = h->keep_n.as<int>(), *new_n = keep_n + (N + 2);
     int *keep_e = h->keep_e.as<int>(), *new_e = keep_e + (E + 2);
@@ -829,9 +841,10 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
         LAUNCH(h, k_component_max, grid_for(N, 256), 256, h->node_cov.as<uint32_t>(), h->node_comp.as<uint32_t>(), N,
                h->comp_max.as<uint32_t>());
     }
-    LAUNCH(h, k_node_keep, grid_for(N + 1, 256), 256, h->node_cov.as<uint32_t>(), h->node_comp.as<uint32_t>(),
-           h->comp_max.as<uint32_t>(), N, thr_node, mode, keep_n);
-    if (mode == 1 && E > 0) {
+    if (mode != 2)
+        LAUNCH(h, k_node_keep, grid_for(N + 1, 256), 256, h->node_cov.as<uint32_t>(), h->node_comp.as<uint32_t>(),
+               h->comp_max.as<uint32_t>(), N, thr_node, mode, keep_n);
+    if (mode != 0 && E > 0) {
         AMIRA_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int) * ST_COUNT, st));
         LAUNCH(h, k_multi_edge_check, grid_for(N, 256), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(),
                h->adj_edges.as<uint32_t>(), h->adj_off.as<int64_t>(), keep_n, N, h->d_status.as<int>());
@@ -1733,6 +1746,157 @@ int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edg
 int amira_gmg_debug_layout(amira_gmg *h, int mask) {
     AMIRA_TRY(check_handle(h));
     h->force_layout = mask;
+    return AMIRA_OK;
+}
+
+// ---- post-build scans (stats.cuh) ---------------------------------------------------------------------
+namespace {
+int stats_ready(amira_gmg *h) {
+    AMIRA_TRY(check_handle(h));
+    if (!h->built) {
+        set_error("no graph on this handle");
+        return AMIRA_E_STATE;
+    }
+    AMIRA_TRY(finish(h, false));
+    return h->built ? AMIRA_OK : h->last_status;
+}
+}  // namespace
+
+int amira_gmg_read_length_coverages(amira_gmg *h, const int32_t *min_len, int32_t n, int64_t *sums) {
+    AMIRA_TRY(stats_ready(h));
+    if (n < 0 || n > STAT_MAX_THRESHOLDS || (n > 0 && (!min_len || !sums))) {
+        set_error("at most %d thresholds", STAT_MAX_THRESHOLDS);
+        return AMIRA_E_ARG;
+    }
+    Thresholds T;
+    T.n = n;
+    for (int i = 0; i < n; ++i) T.min_len[i] = min_len[i];
+    AMIRA_TRY(h->comp_max.reserve(sizeof(unsigned long long) * STAT_MAX_THRESHOLDS));
+    unsigned long long *d_sums = h->comp_max.as<unsigned long long>();
+    AMIRA_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(unsigned long long) * STAT_MAX_THRESHOLDS, h->stream));
+    if (h->n_inc > 0 && n > 0)
+        LAUNCH(h, k_read_length_coverages, (int)std::min<int64_t>(grid_for(h->n_inc, 256), (int64_t)h->n_sm * 16), 256,
+               h->reads_off.as<int64_t>(), h->reads.as<uint32_t>(), h->off, (long long)h->n_inc, (int32_t)h->first_read_global, T,
+               d_sums);
+    unsigned long long out[STAT_MAX_THRESHOLDS];
+    AMIRA_CUDA(cudaMemcpyAsync(out, d_sums, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) sums[i] = (int64_t)out[i];
+    return AMIRA_OK;
+}
+
+int amira_gmg_node_coverage_stats(amira_gmg *h, int64_t *sum_cov, uint32_t *max_cov) {
+    AMIRA_TRY(stats_ready(h));
+    AMIRA_TRY(h->comp_max.reserve(sizeof(unsigned long long) * STAT_MAX_THRESHOLDS));
+    unsigned long long *d = h->comp_max.as<unsigned long long>();
+    AMIRA_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 2, h->stream));
+    if (h->n_nodes > 0)
+        LAUNCH(h, k_coverage_sum, (int)std::min<int64_t>(grid_for(h->n_nodes, 256), (int64_t)h->n_sm * 8), 256,
+               h->node_cov.as<uint32_t>(), (long long)h->n_nodes, d);
+    unsigned long long out[2];
+    AMIRA_CUDA(cudaMemcpyAsync(out, d, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    if (sum_cov) *sum_cov = (int64_t)out[0];
+    if (max_cov) *max_cov = (uint32_t)out[1];
+    return AMIRA_OK;
+}
+
+int amira_gmg_junk_read_mask(amira_gmg *h, double error_rate, uint8_t *mask) {
+    AMIRA_TRY(stats_ready(h));
+    if (h->R == 0) return AMIRA_OK;
+    if (!mask) return AMIRA_E_ARG;
+    AMIRA_TRY(h->scratch_off.reserve((size_t)h->R + 8));
+    LAUNCH(h, k_junk_read_mask, grid_for(h->R, 256), 256, h->win_off.as<int64_t>(), h->win_node.as<int32_t>(),
+           h->is_short.as<uint8_t>(), (long long)h->R, error_rate, h->scratch_off.as<uint8_t>());
+    AMIRA_CUDA(cudaMemcpyAsync(mask, h->scratch_off.p, (size_t)h->R, cudaMemcpyDeviceToHost, h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
+}
+
+namespace {
+// flags[i] = node i holds one of the genes; left on the device in scratch_off (N bytes), ranks in comp_max
+int flag_nodes_containing(amira_gmg *h, const int32_t *ranks, int32_t n) {
+    if (n < 0 || (n > 0 && !ranks)) return AMIRA_E_ARG;
+    const int64_t N = h->n_nodes;
+    AMIRA_TRY(h->scratch_off.reserve((size_t)std::max<int64_t>(N, h->R) + 8));
+    AMIRA_TRY(h->comp_max.reserve(sizeof(int32_t) * (size_t)std::max(n, 1) + sizeof(uint32_t) * (size_t)(h->n_comps + 2)));
+    if (n > 0) AMIRA_CUDA(cudaMemcpyAsync(h->comp_max.p, ranks, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    if (N > 0)
+        LAUNCH(h, k_nodes_containing, grid_for(N, 256), 256, h->node_key.as<int32_t>(), (long long)N, h->k, h->comp_max.as<int32_t>(),
+               n, h->scratch_off.as<uint8_t>());
+    return AMIRA_OK;
+}
+}  // namespace
+
+int amira_gmg_nodes_containing(amira_gmg *h, const int32_t *ranks, int32_t n, uint8_t *flags) {
+    AMIRA_TRY(stats_ready(h));
+    AMIRA_TRY(flag_nodes_containing(h, ranks, n));
+    if (h->n_nodes > 0) {
+        if (!flags) return AMIRA_E_ARG;
+        AMIRA_CUDA(cudaMemcpyAsync(flags, h->scratch_off.p, (size_t)h->n_nodes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    return AMIRA_OK;
+}
+
+int amira_gmg_remove_nodes(amira_gmg *h, const uint8_t *remove_flags) {
+    AMIRA_TRY(check_handle(h));
+    AMIRA_TRY(filter_reserve(h));
+    const int64_t N = h->n_nodes;
+    if (N == 0) return h->last_status = AMIRA_OK;
+    if (!remove_flags) return AMIRA_E_ARG;
+    std::vector<int> keep((size_t)N + 1);
+    for (int64_t i = 0; i < N; ++i) keep[i] = remove_flags[i] ? 0 : 1;
+    keep[N] = 0;
+    AMIRA_CUDA(cudaMemcpyAsync(h->keep_n.p, keep.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice, h->stream));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));  // `keep` goes out of scope
+    return h->last_status = do_filter(h, 2, 0, 0);
+}
+
+int amira_gmg_remove_nodes_without_reads_of(amira_gmg *h, const int32_t *ranks, int32_t n) {
+    AMIRA_TRY(check_handle(h));
+    AMIRA_TRY(filter_reserve(h));
+    const int64_t N = h->n_nodes, R = h->R;
+    if (N == 0) return h->last_status = AMIRA_OK;
+    AMIRA_TRY(flag_nodes_containing(h, ranks, n));
+    // reads of the flagged nodes (byte flags behind the node flags), then the nodes that touch none of them
+    AMIRA_TRY(h->dups.reserve((size_t)R + 8));
+    uint8_t *read_flag = h->dups.as<uint8_t>();
+    AMIRA_CUDA(cudaMemsetAsync(read_flag, 0, (size_t)R + 1, h->stream));
+    LAUNCH(h, k_mark_reads_of_nodes, grid_for(N * 32, 256), 256, h->scratch_off.as<uint8_t>(), h->reads_off.as<int64_t>(),
+           h->reads.as<uint32_t>(), (long long)N, (int32_t)h->first_read_global, read_flag);
+    LAUNCH(h, k_nodes_with_marked_reads, grid_for((N + 1) * 32, 256), 256, read_flag, h->reads_off.as<int64_t>(),
+           h->reads.as<uint32_t>(), (long long)N, (int32_t)h->first_read_global, h->keep_n.as<int>());
+    return h->last_status = do_filter(h, 2, 0, 0);
+}
+
+int amira_gmg_linear_steps(amira_gmg *h, uint32_t *degree, int32_t *fw_next, int8_t *fw_dir, uint8_t *fw_ext, int32_t *bw_next,
+                           int8_t *bw_dir, uint8_t *bw_ext) {
+    AMIRA_TRY(stats_ready(h));
+    const int64_t N = h->n_nodes;
+    if (N == 0) return AMIRA_OK;
+    // [degree u32][next fw i32][next bw i32][dir fw i8][dir bw i8][ext fw u8][ext bw u8] per node
+    AMIRA_TRY(h->keep_e.reserve((size_t)N * 16 + 64));
+    char *base = h->keep_e.as<char>();
+    LinearSteps S;
+    S.degree = (uint32_t *)base;
+    S.next[0] = (int32_t *)(base + 4 * N);
+    S.next[1] = (int32_t *)(base + 8 * N);
+    S.dir[0] = (int8_t *)(base + 12 * N);
+    S.dir[1] = (int8_t *)(base + 13 * N);
+    S.ext[0] = (uint8_t *)(base + 14 * N);
+    S.ext[1] = (uint8_t *)(base + 15 * N);
+    LAUNCH(h, k_linear_steps, grid_for(N, 256), 256, h->adj_off.as<int64_t>(), h->adj_edges.as<uint32_t>(), h->e_tgt.as<int32_t>(),
+           h->e_td.as<int8_t>(), (long long)N, S);
+    AMIRA_TRY(d2h(h, degree, S.degree, sizeof(uint32_t) * N));
+    AMIRA_TRY(d2h(h, fw_next, S.next[0], sizeof(int32_t) * N));
+    AMIRA_TRY(d2h(h, bw_next, S.next[1], sizeof(int32_t) * N));
+    AMIRA_TRY(d2h(h, fw_dir, S.dir[0], N));
+    AMIRA_TRY(d2h(h, bw_dir, S.dir[1], N));
+    AMIRA_TRY(d2h(h, fw_ext, S.ext[0], N));
+    AMIRA_TRY(d2h(h, bw_ext, S.ext[1], N));
+    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    h->filt_N = h->filt_E = -1;  // keep_e was the edge mask of the last filter
     return AMIRA_OK;
 }
 

@@ -86,6 +86,49 @@ class DeviceGraph:
     def remove_low_coverage_components(self, min_component_cov: int):
         _lib.check(self._lib.amira_gmg_remove_low_coverage_components(self._h, int(min_component_cov)))
 
+    # ---- post-build scans on the device-resident graph (include/amira_gmg.h) ----------
+    def read_length_coverages(self, min_lens) -> np.ndarray:
+        """sums[i] = number of (node, read) incidences whose read has >= min_lens[i] gene calls"""
+        ml = np.ascontiguousarray(min_lens, np.int32)
+        out = np.zeros(len(ml), np.int64)
+        _lib.check(self._lib.amira_gmg_read_length_coverages(self._h, _ptr(ml), len(ml), _ptr(out)))
+        return out
+
+    def node_coverage_stats(self):
+        s, m = C.c_int64(), C.c_uint32()
+        _lib.check(self._lib.amira_gmg_node_coverage_stats(self._h, C.byref(s), C.byref(m)))
+        return s.value, m.value
+
+    def junk_read_mask(self, error_rate: float) -> np.ndarray:
+        """1 = kept, 0 = rejected, 2 = short read (upstream remove_junk_reads)"""
+        mask = np.zeros(self.R, np.uint8)
+        _lib.check(self._lib.amira_gmg_junk_read_mask(self._h, float(error_rate), _ptr(mask)))
+        return mask
+
+    def nodes_containing(self, ranks) -> np.ndarray:
+        r = np.ascontiguousarray(ranks, np.int32)
+        flags = np.zeros(self.sizes_early()["nodes"], np.uint8)
+        _lib.check(self._lib.amira_gmg_nodes_containing(self._h, _ptr(r), len(r), _ptr(flags)))
+        return flags.astype(bool)
+
+    def remove_nodes(self, remove_flags):
+        f = np.ascontiguousarray(remove_flags, np.uint8)
+        assert len(f) == self.sizes_early()["nodes"]
+        _lib.check(self._lib.amira_gmg_remove_nodes(self._h, _ptr(f)))
+
+    def remove_nodes_without_reads_of(self, ranks):
+        r = np.ascontiguousarray(ranks, np.int32)
+        _lib.check(self._lib.amira_gmg_remove_nodes_without_reads_of(self._h, _ptr(r), len(r)))
+
+    def linear_steps(self) -> dict:
+        n = self.sizes()["nodes"]
+        a = {"degree": np.zeros(n, np.uint32), "fw_next": np.zeros(n, np.int32), "fw_dir": np.zeros(n, np.int8),
+             "fw_ext": np.zeros(n, np.uint8), "bw_next": np.zeros(n, np.int32), "bw_dir": np.zeros(n, np.int8),
+             "bw_ext": np.zeros(n, np.uint8)}
+        _lib.check(self._lib.amira_gmg_linear_steps(self._h, *[_ptr(a[f]) for f in ("degree", "fw_next", "fw_dir", "fw_ext",
+                                                                                     "bw_next", "bw_dir", "bw_ext")]))
+        return a
+
     def filter_masks(self):
         """keep flags of the last filter / component removal, indexed by the pre-filter node / edge order"""
         a, b = C.c_int64(), C.c_int64()

@@ -146,6 +146,31 @@ int amira_gmg_filter(amira_gmg *h, uint32_t min_node_cov, uint32_t min_edge_cov)
 int amira_gmg_filter_mask_sizes(amira_gmg *h, int64_t *n_nodes_before, int64_t *n_edges_before);
 int amira_gmg_export_filter_masks(amira_gmg *h, int32_t *node_keep, int32_t *edge_keep);
 
+/* ---- the scans Amira runs right after a build, on the device-resident graph ----
+ * read_length_coverages: get_overall_mean_node_coverages (graph_utils.py:299-313): sums[i] = number of
+ *   (node, read) incidences whose read has >= min_len[i] gene calls (mean node coverage = sums[i] / n_nodes);
+ *   at most 16 thresholds.
+ * node_coverage_stats: sum and maximum of Node.nodeCoverage (get_all_node_coverages / get_mean_node_coverage,
+ *   construct_graph.py:863-871).
+ * junk_read_mask: remove_junk_reads (construct_graph.py:1398-1420): mask[r] = 1 kept, 0 rejected (more than
+ *   round(n * (1 - error_rate)) of the read's n windows are None; Python's round-half-even), 2 = short read.
+ * nodes_containing: get_nodes_containing (construct_graph.py:223-244) for a set of genes given by rank (1..V).
+ * remove_nodes: remove_node (construct_graph.py:463-484) for every node whose flag is set (host flags[n_nodes]):
+ *   edges, per-read windows (None) and _readsToCorrect follow as in the filters; AMIRA_E_MULTI_EDGE like upstream.
+ * remove_nodes_without_reads_of: remove_non_AMR_associated_nodes (construct_graph.py:2941-2959).
+ * linear_steps: the building block of get_linear_path_for_node / remove_short_linear_paths / get_unitigs_in_graph
+ *   (construct_graph.py:722-861, 679-720, 2961-2975): Node degree and, per node and side (forward / backward),
+ *   upstream's one step along a linear path: next node (-1 none), direction in which it is entered, and whether
+ *   the walk continues (target of degree 1 or 2, not the node itself). */
+int amira_gmg_read_length_coverages(amira_gmg *h, const int32_t *min_len, int32_t n, int64_t *sums);
+int amira_gmg_node_coverage_stats(amira_gmg *h, int64_t *sum_cov, uint32_t *max_cov);
+int amira_gmg_junk_read_mask(amira_gmg *h, double error_rate, uint8_t *mask);
+int amira_gmg_nodes_containing(amira_gmg *h, const int32_t *ranks, int32_t n, uint8_t *flags);
+int amira_gmg_remove_nodes(amira_gmg *h, const uint8_t *remove_flags);
+int amira_gmg_remove_nodes_without_reads_of(amira_gmg *h, const int32_t *ranks, int32_t n);
+int amira_gmg_linear_steps(amira_gmg *h, uint32_t *degree, int32_t *fw_next, int8_t *fw_dir, uint8_t *fw_ext,
+                           int32_t *bw_next, int8_t *bw_dir, uint8_t *bw_ext);
+
 /* Multi-GPU (one process per GPU; no upstream counterpart -- upstream's joblib fan-out,
  * graph_utils.py:105-124, is disabled at every call site).  The globally ordered read set is
  * sharded contiguously over ranks in rank order; canonical gene-mers and edges are owned by hash
