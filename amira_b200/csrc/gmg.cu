@@ -514,7 +514,8 @@ int enqueue_order(amira_gmg *h) {
         Phase ph(h, AMIRA_PH_EMIT_NODES);
         LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->nview, h->ids, h->k, bm_node,
                h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(), h->node_dir.as<int8_t>(),
-               h->parent.as<int32_t>(), h->node_src.as<uint32_t>());
+               h->parent.as<int32_t>(), h->node_src.as<uint32_t>(),
+               (h->n16 && h->key_bits > 0) ? h->ntab.as<NodeSlot16>() : (const NodeSlot16 *)nullptr, h->key_bits);
     }
     return AMIRA_OK;
 }

@@ -134,6 +134,33 @@ __device__ __forceinline__ unsigned long long packed_hash(unsigned long long klo
     return h;
 }
 
+// 32-bit bucket hash of a packed key of at most 85 bits (the 16-byte layout: the key itself is the identity, the
+// hash only picks the bucket): 32-bit multiplies instead of the three 64-bit ones of packed_hash
+__device__ __forceinline__ unsigned int packed_hash32(unsigned long long klo, unsigned long long khi) {
+    unsigned int h = (unsigned int)klo * 0x9E3779B1u;
+    h ^= h >> 15;
+    h += (unsigned int)(klo >> 32) * 0x85EBCA77u;
+    h ^= h >> 13;
+    h += (unsigned int)khi * 0xC2B2AE3Du;
+    h *= 0x27D4EB2Fu;
+    h ^= h >> 16;
+    h *= 0x165667B1u;
+    h ^= h >> 15;
+    return h;
+}
+
+__device__ __forceinline__ unsigned int edge_hash32(unsigned long long key) {
+    unsigned int h = (unsigned int)key * 0x9E3779B1u;
+    h ^= h >> 15;
+    h += (unsigned int)(key >> 32) * 0x85EBCA77u;
+    h ^= h >> 13;
+    h *= 0x27D4EB2Fu;
+    h ^= h >> 16;
+    h *= 0x165667B1u;
+    h ^= h >> 15;
+    return h;
+}
+
 // one 256-bit load of a node slot (LDG.E.256): word, cov|aux, packed key halves
 __device__ __forceinline__ void load_node_slot(const NodeSlot *s, unsigned long long &word, unsigned long long &ca,
                                                unsigned long long &klo, unsigned long long &khi) {
@@ -281,10 +308,7 @@ __device__ __forceinline__ unsigned int node_insert16(const BuildParams &P, cons
 
 __device__ __forceinline__ void edge_insert16(const BuildParams &P, unsigned long long key, unsigned int ord) {
     const unsigned int nb = P.ecap >> 1;
-    unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
-    h ^= h >> 32;
-    h *= 0xD6E8FEB86659FD93ULL;
-    unsigned int b = (unsigned int)(((h >> 32) * nb) >> 32);
+    unsigned int b = (unsigned int)(((unsigned long long)edge_hash32(key) * nb) >> 32);
     const unsigned int max_probe = min(MAX_PROBES, nb);
     for (unsigned int probe = 0; probe < max_probe; ++probe) {
         EdgeSlot16 *B = P.etab16 + 2 * (size_t)b;
@@ -462,7 +486,8 @@ __global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(
                     P.status[ST_ERR] = AMIRA_E_PALINDROME;  // construct_gene_mer.py:23-25
                 } else {
                     const int dirneg = dir < 0;
-                    h = packed ? packed_hash(klo, khi) : canonical_hash(win, k, dirneg);
+                    h = packed ? (N16 ? (unsigned long long)packed_hash32(klo, khi) : packed_hash(klo, khi))
+                               : canonical_hash(win, k, dirneg);
                     unsigned int slot;
                     if (N16) {
                         // the key's bits 63..84 take the place of the fingerprint

@@ -129,7 +129,7 @@ __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids,
                              const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
                              int32_t *__restrict__ node_key, uint32_t *__restrict__ node_cov,
                              int8_t *__restrict__ node_dir, int32_t *__restrict__ parent,
-                             uint32_t *__restrict__ node_src) {
+                             uint32_t *__restrict__ node_src, const NodeSlot16 *__restrict__ tab16, const int key_bits) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
         unsigned long long w = nv.w(s);
@@ -142,8 +142,25 @@ __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids,
         node_src[idx] = nv.base(s);
         node_dir[idx] = neg ? -1 : 1;
         parent[idx] = idx;
-        for (int j = 0; j < k; ++j)
-            node_key[(int64_t)idx * k + j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
+        if (tab16) {
+            // 16-byte slots: the canonical gene-mer is in the slot (top 22 bits in `word`, low 63 in `key`), no need
+            // to go back to the ids
+            const unsigned long long top = w >> FP_SHIFT, keylow = tab16[s].key;
+            const unsigned long long klo = keylow | ((top & 1ull) << 63), khi = top >> 1;
+            const unsigned long long mask = (1ull << key_bits) - 1ull;
+            const int bias = 1 << (key_bits - 1);
+            for (int j = 0; j < k; ++j) {
+                const int sh = (k - 1 - j) * key_bits;
+                unsigned long long f;
+                if (sh >= 64) f = khi >> (sh - 64);
+                else if (sh == 0) f = klo;
+                else f = (klo >> sh) | (khi << (64 - sh));
+                node_key[(int64_t)idx * k + j] = (int)(f & mask) - bias;
+            }
+        } else {
+            for (int j = 0; j < k; ++j)
+                node_key[(int64_t)idx * k + j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
+        }
     }
 }
 

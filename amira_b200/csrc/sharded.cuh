@@ -184,7 +184,7 @@ __device__ __forceinline__ long long node_find_local(const BuildParams &L, bool 
             khi = (khi << kb) | (klo >> (64 - kb));
             klo = (klo << kb) | (unsigned long long)u;
         }
-        const unsigned long long h = packed_hash(klo, khi);
+        const unsigned long long h = n16 ? (unsigned long long)packed_hash32(klo, khi) : packed_hash(klo, khi);
         if (n16) {
             const unsigned int nb = L.ncap >> 1;
             unsigned int b = (unsigned int)(((unsigned long long)(unsigned int)h * nb) >> 32);

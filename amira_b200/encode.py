@@ -172,5 +172,55 @@ class EncodedReads:
         self.positions = None
         if self.pos_start is not None:
             ps, pe = self.pos_start.tolist(), self.pos_end.tolist()
-            self.positions = {r: [(ps[j], pe[j]) for j in range(off[i], off[i + 1])] for i, r in enumerate(self.read_ids)}
+            # encode_reads stores (-1, -1) for the calls of a read whose positions entry is empty: back to []
+            self.positions = {r: ([] if off[i + 1] > off[i] and all(ps[j] == -1 and pe[j] == -1 for j in range(off[i], off[i + 1]))
+                                  else [(ps[j], pe[j]) for j in range(off[i], off[i + 1])])
+                              for i, r in enumerate(self.read_ids)}
         return self
+
+    def update(self, changed: dict, positions: dict | None = None):
+        """Re-encode only the reads in `changed` ({read_id: new gene calls}; the rebuild-after-correction loop of
+        iterative_bubble_popping, amira/graph_utils.py:127-181, rewrites a few reads per iteration): the other reads
+        keep their encoded calls, the CSR is spliced, and the vocabulary is re-ranked only if a new gene name appears.
+        Returns a new EncodedReads over the same (updated in place) read dict."""
+        for r in changed:
+            if r not in self.reads:
+                raise KeyError(r)
+        new_names = collect_names(changed) - set(self.vocab.names)
+        self.reads.update(changed)
+        if positions:
+            if self.positions is None:
+                self.positions = {}
+            self.positions.update(positions)
+        if new_names or (positions and self.pos_start is None):
+            return EncodedReads(self.reads, self.positions)          # ranks shift: everything is re-encoded
+        sub_ids, sub_off, sub_ps, sub_pe = encode_reads(changed, self.vocab, positions if self.pos_start is not None else None)
+        index = {r: i for i, r in enumerate(self.read_ids)}
+        lens = np.diff(self.off)
+        order = [index[r] for r in changed]
+        lens[order] = np.diff(sub_off)
+        off = np.zeros(len(self.read_ids) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        out = EncodedReads.__new__(EncodedReads)
+        out.reads, out.positions, out.read_ids, out.vocab, out._device = self.reads, self.positions, self.read_ids, self.vocab, None
+        out.off = off
+        changed_at = dict(zip(order, range(len(order))))
+
+        def splice(old, sub):
+            if old is None:
+                return None
+            new = np.empty(int(off[-1]), old.dtype)
+            # unchanged reads in runs between the changed ones
+            prev = 0
+            for i in sorted(changed_at) + [len(self.read_ids)]:
+                if i > prev:
+                    new[off[prev]:off[i]] = old[self.off[prev]:self.off[i]]
+                if i < len(self.read_ids):
+                    j = changed_at[i]
+                    new[off[i]:off[i + 1]] = sub[sub_off[j]:sub_off[j + 1]]
+                prev = i + 1
+            return new
+        out.ids = splice(self.ids, sub_ids)
+        out.pos_start = splice(self.pos_start, sub_ps if sub_ps is not None else None)
+        out.pos_end = splice(self.pos_end, sub_pe if sub_pe is not None else None)
+        return out

@@ -13,6 +13,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: takes more than a few seconds on CPU")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device: on a box without one they are skipped instead of failing"""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_expected():
     import json

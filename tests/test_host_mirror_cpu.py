@@ -224,3 +224,22 @@ def test_post_build_statistics_match_upstream(fake_device):
         assert g.remove_junk_reads(rate) == theirs.remove_junk_reads(rate)
     assert g.get_valid_reads_only() == theirs.get_valid_reads_only()
     assert amira_b200.get_overall_mean_node_coverages(g) == up_gu.get_overall_mean_node_coverages(theirs)
+
+
+def test_encoded_reads_round_trip_and_incremental_update(tmp_path):
+    reads = {"r1": ["+a", "-b", "+c", "+d"], "r2": ["-d", "+b"], "r3": [], "r4": ["+e", "+a", "-c"]}
+    pos = {"r1": [[1, 2], [3, 4], [5, 6], [7, 8]], "r2": [], "r3": [], "r4": [[1, 9], [10, 19], [20, 29]]}
+    enc = encode.EncodedReads(dict(reads), dict(pos))
+    enc.save(str(tmp_path / "calls.npz"))
+    back = encode.EncodedReads.load(str(tmp_path / "calls.npz"))
+    assert back.reads == reads and back.ids.tolist() == enc.ids.tolist() and back.off.tolist() == enc.off.tolist()
+    assert back.positions["r2"] == [] and back.positions["r1"] == [(1, 2), (3, 4), (5, 6), (7, 8)]
+    # incremental re-encode: same arrays as a fresh encoding of the edited dict, known genes only -> spliced
+    enc2 = encode.EncodedReads(dict(reads))
+    upd = enc2.update({"r2": ["+a", "+a", "-e"], "r4": ["+b"]})
+    fresh = encode.EncodedReads(dict(enc2.reads))
+    assert upd.ids.tolist() == fresh.ids.tolist() and upd.off.tolist() == fresh.off.tolist()
+    assert upd.vocab.names == fresh.vocab.names
+    upd2 = upd.update({"r1": ["+zzz_new_gene", "-a"]})          # a new gene re-ranks the vocabulary
+    fresh2 = encode.EncodedReads(dict(upd.reads))
+    assert upd2.ids.tolist() == fresh2.ids.tolist() and upd2.vocab.names == fresh2.vocab.names
