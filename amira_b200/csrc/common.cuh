@@ -129,8 +129,8 @@ constexpr int KEY16_BITS = 85;       // 63 in NodeSlot16::key + 22 in the finger
 constexpr int ORD32_P_BITS = 30;
 
 // layout-independent view of the local node table for the passes after the insert
-// info[slot] = {node index once the first-seen order is known, start of the slot's raw node -> reads segment}:
-// one 8-byte gather per window in the scatter pass
+// info[slot] = {node index once the first-seen order is known, unit of that node's read list (incidence.cuh)}:
+// one 8-byte gather per window in the partition pass
 struct NodeView {
     unsigned long long *word;
     unsigned int *cov;

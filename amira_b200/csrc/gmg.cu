@@ -74,10 +74,12 @@ struct amira_gmg {
     // per read / per tile
     DevBuf win_off, is_short, to_correct, tile_r0;
     // per window
-    DevBuf win_slot, win_node, win_dir, win_rank, win_read, win_start, win_end;  // win_slot: table slots from the insert kernel; win_node: node indices
-    int64_t scatter_l2_bytes = 40ll << 20;  // raw read lists one scatter pass may touch (stays in L2)
+    DevBuf win_slot, win_node, win_dir, win_read, win_start, win_end;  // win_slot: table slots from the insert kernel; win_node: node indices
+    // node -> reads transpose (incidence.cuh): (node, read) records dealt into buckets, first node of every unit
+    DevBuf inc_rec, unit_lo, bucket_cursor;
+    UnitPlan unit_plan = {};
     // hash tables + first-seen bitmaps
-    DevBuf ntab, etab, slot_info, node_src, bitmaps, cnt_node, cnt_edge;
+    DevBuf ntab, etab, slot_info, bitmaps, cnt_node, cnt_edge;
     unsigned int ncap = 0, ecap = 0;
     int key_bits = 0;
     int64_t grow_n = 1, grow_e = 1;     // capacity multipliers after an overflow
@@ -184,7 +186,10 @@ int cub_call(amira_gmg *h, F f) {
 // launches inside this scope go to the second stream
 struct SideStream {
     amira_gmg *h;
-    explicit SideStream(amira_gmg *h_) : h(h_) { h->cur = h->stream2; }
+    explicit SideStream(amira_gmg *h_) : h(h_) {
+        static const bool one_stream = getenv("AMIRA_ONE_STREAM") != nullptr;  // developer experiments: clean per-phase times
+        h->cur = one_stream ? h->stream : h->stream2;
+    }
     ~SideStream() { h->cur = h->stream; }
 };
 
@@ -350,7 +355,6 @@ int plan_build(amira_gmg *h) {
     AMIRA_TRY(h->win_slot.reserve(sizeof(int32_t) * gcap + 32));
     AMIRA_TRY(h->win_node.reserve(sizeof(int32_t) * gcap + 32));
     AMIRA_TRY(h->win_dir.reserve(gcap));
-    AMIRA_TRY(h->win_rank.reserve(sizeof(uint32_t) * gcap + 32));
     AMIRA_TRY(h->win_read.reserve(sizeof(int32_t) * gcap + 32));
     if (h->has_pos) {
         AMIRA_TRY(h->win_start.reserve(sizeof(int32_t) * gcap));
@@ -377,7 +381,6 @@ int reserve_graph(amira_gmg *h, int64_t capN, int64_t capE) {
     AMIRA_TRY(h->is_root.reserve(sizeof(int) * (capN + 2)));
     AMIRA_TRY(h->cc_min.reserve(sizeof(unsigned int) * (capN + 1)));
     AMIRA_TRY(h->reads_off.reserve(sizeof(int64_t) * (capN + 2)));
-    AMIRA_TRY(h->node_src.reserve(sizeof(uint32_t) * (capN + 2)));
     AMIRA_TRY(h->dups.reserve(sizeof(uint32_t) * (capN + 1)));
     AMIRA_TRY(h->reads.reserve(sizeof(uint32_t) * G));
     AMIRA_TRY(h->e_src.reserve(sizeof(int32_t) * (capE + 2)));
@@ -390,6 +393,21 @@ int reserve_graph(amira_gmg *h, int64_t capN, int64_t capE) {
     AMIRA_TRY(h->adj_edges.reserve(sizeof(uint32_t) * (capE + 1)));
     AMIRA_TRY(h->adj_tmp.reserve(sizeof(uint32_t) * (capE + 1)));
     AMIRA_TRY(h->reads_tmp.reserve(sizeof(uint32_t) * G));
+    AMIRA_TRY(h->inc_rec.reserve(sizeof(uint2) * (size_t)G));
+    {
+        // units of the node -> reads transpose: upper bound from the call count and the node capacity; more than
+        // INC_NB_MAX of them share buckets (a unit then sweeps its whole bucket)
+        UnitPlan &u = h->unit_plan;
+        const int64_t n_max = h->G / INC_C + std::min<int64_t>(capN, h->world > 1 ? capN : std::max<int64_t>(h->G, 1)) / INC_S + 2;
+        u.g = 0;
+        while (((n_max + (1ll << u.g) - 1) >> u.g) > INC_NB_MAX) ++u.g;
+        u.n_buckets = (int)((n_max + (1ll << u.g) - 1) >> u.g);
+        u.n_units = u.n_buckets << u.g;
+        u.read_lo = (uint32_t)h->first_read_global;
+        u.rscale = (uint32_t)(0xFFFFFFFFull / (unsigned long long)std::max<int64_t>(R, 1));
+        AMIRA_TRY(h->unit_lo.reserve(sizeof(int) * ((size_t)u.n_units + 2)));
+        AMIRA_TRY(h->bucket_cursor.reserve(sizeof(unsigned int) * 2 * INC_NB_MAX));  // cursors, then region starts
+    }
     for (int i = 0; i < 2; ++i)  // either stream may sort either array (the filter rebuilds the adjacency on the main one)
         AMIRA_TRY(h->seg_work[i].reserve(sizeof(long long) * (size_t)(std::max<int64_t>(G, capE) / SEG_BITONIC_MAX + 64 + 2)));
     const int64_t scan_max = std::max<int64_t>(std::max<int64_t>(R + 2, n_words + 2), std::max<int64_t>(2 * capN + 3, capE + 2));
@@ -440,7 +458,6 @@ int enqueue_insert(amira_gmg *h) {
     P.ntab = h->ntab.as<NodeSlot>(); P.ntab16 = h->ntab.as<NodeSlot16>(); P.ncov = h->nview.cov;
     P.ncap = h->ncap; P.etab = h->etab.as<EdgeSlot>(); P.etab16 = h->etab.as<EdgeSlot16>(); P.ecap = h->ecap;
     P.win_node = h->win_slot.as<int32_t>(); P.win_dir = h->win_dir.as<int8_t>();
-    P.win_rank = h->win_rank.as<uint32_t>();
     P.win_read = h->win_read.as<int32_t>();
     P.win_start = h->has_pos ? h->win_start.as<int32_t>() : nullptr;
     P.win_end = h->has_pos ? h->win_end.as<int32_t>() : nullptr;
@@ -488,8 +505,6 @@ int enqueue_insert(amira_gmg *h) {
         if (e16) LAUNCH(h, k_boundary_edges<true>, grid_for(n_tiles - 1, 256), 256, P);
         else LAUNCH(h, k_boundary_edges<false>, grid_for(n_tiles - 1, 256), 256, P);
     }
-    // where every slot's raw read list starts (table order)
-    AMIRA_TRY(run_scan(h, SlotBaseLoad{h->nview}, SlotBaseStore{h->nview}, nullptr, 1, h->ncap, h->ncap));
     return AMIRA_OK;
 }
 
@@ -514,7 +529,7 @@ int enqueue_order(amira_gmg *h) {
         Phase ph(h, AMIRA_PH_EMIT_NODES);
         LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->nview, h->ids, h->k, bm_node,
                h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(), h->node_dir.as<int8_t>(),
-               h->parent.as<int32_t>(), h->node_src.as<uint32_t>(),
+               h->parent.as<int32_t>(),
                (h->n16 && h->key_bits > 0) ? h->ntab.as<NodeSlot16>() : (const NodeSlot16 *)nullptr, h->key_bits);
     }
     return AMIRA_OK;
@@ -565,29 +580,50 @@ int enqueue_tail(amira_gmg *h) {
         AMIRA_CUDA(cudaEventRecord(h->ev_join, h->cur));
     }
     {
-        // node -> reads: coverage per node (counted by the insert kernel) -> segment offsets + cursors
+        // node -> reads (incidence.cuh): coverage per node (counted by the insert kernel) -> offsets, units,
+        // records dealt into buckets (the same pass writes the per-read node lists), one CTA per unit
         const uint32_t *cov = h->world > 1 ? h->cov_local.as<uint32_t>() : h->node_cov.as<uint32_t>();
+        const UnitPlan &u = h->unit_plan;
         {
             Phase ph(h, AMIRA_PH_REMAP);
             AMIRA_TRY(run_scan(h, CovLoad{cov}, CovStore{h->reads_off.as<int64_t>(), N, dsz(h, 0)}, dsz(h, SZ_NODES), 1, 0,
                                h->cap_nodes));
-            // one pass per slot range whose raw lists fit L2 (see k_scatter_windows); the first one also writes the
-            // per-read node lists into the second window array
-            const int n_pass = (int)std::min<int64_t>(8, std::max<int64_t>(1, (4 * G + h->scatter_l2_bytes - 1) / h->scatter_l2_bytes));
-            const int sgrid = (int)std::min<int64_t>(grid_for((G + 3) / 4, 256), (int64_t)h->n_sm * 16);
-            for (int p = 0; p < n_pass; ++p) {
-                const unsigned int lo = (unsigned int)((uint64_t)h->ncap * p / n_pass), hi = (unsigned int)((uint64_t)h->ncap * (p + 1) / n_pass);
-                LAUNCH(h, k_scatter_windows, sgrid, 256, h->nview, h->win_slot.as<int32_t>(),
-                       p == 0 ? h->win_node.as<int32_t>() : (int32_t *)nullptr, h->win_rank.as<uint32_t>(),
-                       h->win_read.as<int32_t>(), (const long long *)h->d_sizes.p, h->reads_tmp.as<uint32_t>(), lo, hi);
-            }
+            LAUNCH(h, k_unit_table, (int)std::min<int64_t>(grid_for(std::max<int64_t>(h->ncap, h->cap_nodes + 1), 256), (int64_t)h->n_sm * 16), 256,
+                   h->nview, h->reads_off.as<int64_t>(), dsz(h, SZ_NODES), u, h->unit_lo.as<int>(), h->d_status.as<int>());
+            unsigned int *bcur = h->bucket_cursor.as<unsigned int>();
+            LAUNCH(h, k_bucket_base, INC_NB_MAX / 256, 256, h->unit_lo.as<int>(), h->reads_off.as<int64_t>(), u, bcur + INC_NB_MAX, bcur);
+            const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PART_TILE - 1) / PART_TILE), (int64_t)h->n_sm * 4);
+            k_partition<<<pgrid, PART_THREADS, 0, st>>>(h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(),
+                                                        h->win_node.as<int32_t>(), (const long long *)h->d_sizes.p, bcur + INC_NB_MAX, u, bcur,
+                                                        h->inc_rec.as<uint2>());
+            h->launches++;
+            AMIRA_CUDA(cudaGetLastError());
         }
         if (!h->capturing) AMIRA_CUDA(cudaEventRecord(h->ev_reads_ready, st));
         Phase ph(h, AMIRA_PH_INCIDENCE);
+        // in-place job over `reads` for the units that outgrow shared memory (and the lists they leave to the
+        // work-list kernels of segsort.cuh)
+        DevBuf &wb = h->seg_work[0];
+        const int64_t wcap = std::max<int64_t>(G, 1) / SEG_BITONIC_MAX + 64;
+        SegWork work{wb.as<unsigned int>(), wb.as<long long>() + 1, wcap};
+        AMIRA_CUDA(cudaMemsetAsync(wb.p, 0, sizeof(long long), st));
+        h->lib_launches++;
         const int64_t reads_global = h->world > 1 ? 0x7FFFFFF0ll : h->R;
-        AMIRA_TRY(run_segsort(h, h->reads_tmp.as<uint32_t>(), h->reads.as<uint32_t>(), h->reads_off.as<int64_t>(),
-                              h->node_src.as<uint32_t>(), true, dsz(h, SZ_NODES), 1, h->cap_nodes, std::max<int64_t>(G, 1), reads_global + 1,
-                              h->dups.as<uint32_t>(), (unsigned long long *)dsz(h, SZ_DUPS)));
+        const int bits = bits_for64(std::max<int64_t>(reads_global + 1, 2));
+        SegJob J;
+        J.a = h->reads.as<uint32_t>(); J.b = h->reads_tmp.as<uint32_t>(); J.off = h->reads_off.as<int64_t>(); J.a_start = nullptr;
+        J.n_seg_ptr = dsz(h, SZ_NODES); J.seg_mul = 1;
+        J.dups = h->dups.as<uint32_t>(); J.total_dups = (unsigned long long *)dsz(h, SZ_DUPS);
+        J.passes = bits <= 2 * SEG_MAX_DIGIT_BITS ? 2 : 4;
+        J.digit_bits = std::max(5, (bits + J.passes - 1) / J.passes);
+        k_unit_lists<<<u.n_units, INC_THREADS, INC_SMEM, st>>>(h->inc_rec.as<uint2>(), h->unit_lo.as<int>(), u, J, work);
+        h->launches++;
+        AMIRA_CUDA(cudaGetLastError());
+        LAUNCH(h, k_segsort_warp, (int)std::min<int64_t>((wcap + 3) / 4, (int64_t)h->n_sm * 4), 128, J, work);
+        const size_t cnt_bytes = sizeof(unsigned int) * SEG_RADIX_WARPS * ((size_t)1 << J.digit_bits);
+        k_segsort_radix<<<(int)std::min<int64_t>(wcap, (int64_t)h->n_sm * 3), SEG_RADIX_THREADS, cnt_bytes, st>>>(J, work, 0);
+        h->launches++;
+        AMIRA_CUDA(cudaGetLastError());
     }
     AMIRA_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     AMIRA_TRY(enqueue_report(h, 1));
@@ -1154,7 +1190,7 @@ int sharded_merge(amira_gmg *h) {
         // local slots -> global node indices: probe the rank's own node table with every global gene-mer
         if (h->G > 0)
             LAUNCH(h, k_global_to_local, grid_for(Ng, 256), 256, h->local_P, h->n16 ? 1 : 0, h->nview,
-                   h->node_key.as<int32_t>(), (long long)Ng, h->cov_local.as<uint32_t>(), h->node_src.as<uint32_t>());
+                   h->node_key.as<int32_t>(), (long long)Ng, h->cov_local.as<uint32_t>());
     }
 
     tr.mark("n_global");
@@ -1333,8 +1369,7 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     cudaDeviceProp prop;
     AMIRA_CUDA(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
-    if (prop.l2CacheSize > 0) h->scatter_l2_bytes = std::max<int64_t>(8ll << 20, (int64_t)prop.l2CacheSize / 3);
-    if (const char *e = getenv("AMIRA_SCATTER_MB")) h->scatter_l2_bytes = std::max<int64_t>(1, atoll(e)) << 20;  // developer experiments
+    AMIRA_CUDA(cudaFuncSetAttribute(k_unit_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INC_SMEM));
     int occ = 1;
     AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_insert_windows<5, true, true>), INS_THREADS, 0));
     h->insert_ctas_per_sm = std::max(1, occ);
@@ -1375,7 +1410,7 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->reads_off, &h->reads, &h->node_key2, &h->node_cov2, &h->node_dir2, &h->node_comp2,
                       &h->reads_off2, &h->reads2, &h->parent, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
                       &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
-                      &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->node_src, &h->win_rank, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->dups,
+                      &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->inc_rec, &h->unit_lo, &h->bucket_cursor, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->dups,
                       &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,
                       &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rkey2, &h->x_rmeta2,
                       &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_sortk, &h->x_sortk2, &h->x_sorti,

@@ -69,7 +69,6 @@ struct BuildParams {
     unsigned int ecap;
     int32_t *win_node;
     int8_t *win_dir;
-    uint32_t *win_rank;  // arrival rank of the window among the windows of its node (0-based)
     int32_t *win_read;   // read of the window (global index)
     int32_t *win_start;
     int32_t *win_end;
@@ -430,10 +429,6 @@ __global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(
         __syncwarp();
 
         // ---- windows (the pair that straddles two chunks is left to k_boundary_edges)
-        // The coverage atomic returns the window's arrival rank one L2 round trip later: the rank is stored one
-        // iteration late, after the next window's probe has come back, so that nothing waits for it.
-        long long pend_w = -1;
-        unsigned int pend_before = 0;
 #pragma unroll 1
         for (int pl = lane; pl < len; pl += 32) {
             const bool halo = false;
@@ -501,19 +496,16 @@ __global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(
                         slot = node_insert(P, win, dirneg, packed, klo, khi, h, mine);
                     }
                     val = slot | ((unsigned int)dirneg << 31);
-                    if (pend_w >= 0) __stcs(&P.win_rank[pend_w], pend_before + 1u);
                     if (!halo) {
-                        // Node.nodeCoverage: one per window (counts from 0xFFFFFFFF); the value before the increment
-                        // is this window's place in the node's raw read list
-                        const unsigned int before = atomicAdd(N16 ? &P.ncov[slot] : &P.ntab[slot].cov, 1u);
+                        // Node.nodeCoverage: one per window (counts from 0xFFFFFFFF), fire and forget; it sizes the
+                        // node's read list (incidence.cuh)
+                        atomicAdd(N16 ? &P.ncov[slot] : &P.ntab[slot].cov, 1u);
                         const long long rs = (j <= NR_STAGE + 1) ? S.off[j] : P.off[r_lo + j];
                         const long long wo = (j <= NR_STAGE) ? S.woff[j] : P.win_off[r_lo + j];
                         const int64_t w = wo + (p - rs);
                         __stcs(&P.win_node[w], (int32_t)slot);  // streaming stores: keep the tables in L2
                         __stcs(&P.win_dir[w], (signed char)dir);
                         __stcs(&P.win_read[w], (int32_t)(P.read_base + r_lo + j));
-                        pend_w = w;
-                        pend_before = before;
                         if (P.ps) {
                             P.win_start[w] = __ldg(P.ps + p);
                             P.win_end[w] = __ldg(P.pe + p + k - 1);
@@ -523,7 +515,6 @@ __global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(
             }
             S.val[pl] = val;
         }
-        if (pend_w >= 0) __stcs(&P.win_rank[pend_w], pend_before + 1u);
         __syncwarp();
         // ---- adjacent pairs of the same read
 #pragma unroll 1

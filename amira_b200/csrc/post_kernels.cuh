@@ -9,6 +9,7 @@
 #pragma once
 
 #include "gmg_kernels.cuh"
+#include "incidence.cuh"
 
 namespace amira {
 
@@ -111,25 +112,12 @@ struct RankStore {
     }
 };
 
-// start of every slot's raw node -> reads segment: exclusive scan of the window counts in TABLE order (known as
-// soon as the insert kernel is done; the first-seen order is not needed to place the reads)
-struct SlotBaseLoad {
-    NodeView nv;
-    __device__ __forceinline__ unsigned long long operator()(long long i) const { return nv.c((unsigned int)i) + 1u; }
-};
-struct SlotBaseStore {
-    NodeView nv;
-    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const {
-        if (i < (long long)nv.cap) nv.base((unsigned int)i) = (unsigned int)excl;
-    }
-};
-
 // node arrays in first-seen order; node_cov[idx] = windows counted by the insert kernel
 __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids, int k,
                              const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
                              int32_t *__restrict__ node_key, uint32_t *__restrict__ node_cov,
                              int8_t *__restrict__ node_dir, int32_t *__restrict__ parent,
-                             uint32_t *__restrict__ node_src, const NodeSlot16 *__restrict__ tab16, const int key_bits) {
+                             const NodeSlot16 *__restrict__ tab16, const int key_bits) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
         unsigned long long w = nv.w(s);
@@ -139,7 +127,6 @@ __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids,
         const int idx = pref_node[p >> 5] + __popc(bm_node[p >> 5] & ((1u << (p & 31)) - 1u));
         nv.a(s) = (unsigned int)idx;
         node_cov[idx] = nv.c(s) + 1u;
-        node_src[idx] = nv.base(s);
         node_dir[idx] = neg ? -1 : 1;
         parent[idx] = idx;
         if (tab16) {
@@ -245,10 +232,7 @@ __global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
     }
 }
 
-// ---- per-read node lists + node -> reads scatter ------------------------------------------------------
-// One warp per 128-window tile: slot -> node index for the per-read lists (construct_graph.py:165-178)
-// and, on the same pass, the window's read is appended to its node's segment through an atomic cursor
-// (arrival order; k_segsort_main sorts the segments afterwards).
+// ---- node -> reads offsets: exclusive scan of the coverages in node order (the lists themselves: incidence.cuh)
 struct CovLoad {
     const uint32_t *cov;
     __device__ __forceinline__ unsigned long long operator()(long long i) const { return cov[i]; }
@@ -262,60 +246,6 @@ struct CovStore {
         if (i == n.get()) sizes[SZ_INC] = (long long)excl;
     }
 };
-
-// One thread per window, four windows per thread: slot -> (node index, start of the slot's raw list) in one 8-byte
-// gather, the read goes to raw[start + arrival rank], the node index to the per-read list.  The insert kernel left
-// slot, rank and read per window, so the pass is streamed loads, one gather, one scattered store and one streamed
-// store (deriving the read from the offsets instead costs more than the 4 bytes it saves).
-// The raw lists are laid out in table (slot) order, so a slot range is a contiguous piece of `raw`, and the random
-// 4-byte stores only merge into full sectors while that piece stays in L2 (C5 shard, 130 MB of raw lists in one
-// pass: 770 MB of DRAM writes for 260 MB of payload).  So the host runs the pass once per slot range
-// [slot_lo, slot_hi) that fits L2; the pass with node_out != nullptr also writes the per-read node lists (to a
-// second array: the later passes still need the slots).
-__global__ void __launch_bounds__(256) k_scatter_windows(const NodeView nv, const int32_t *__restrict__ win_slot,
-                                                         int32_t *__restrict__ node_out,
-                                                         const uint32_t *__restrict__ win_rank,
-                                                         const int32_t *__restrict__ win_read,
-                                                         const long long *__restrict__ sizes,
-                                                         uint32_t *__restrict__ raw, const unsigned int slot_lo,
-                                                         const unsigned int slot_hi) {
-    const long long W = sizes[SZ_W];
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    const unsigned int span = slot_hi - slot_lo;
-    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; w < W; w += stride) {
-        if (w + 4 <= W) {
-            const int4 v = __ldcs(reinterpret_cast<const int4 *>(win_slot + w));   // streamed: keep the tables in L2
-            const unsigned int sl[4] = {(unsigned int)v.x, (unsigned int)v.y, (unsigned int)v.z, (unsigned int)v.w};
-            bool in[4], any = false;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                in[i] = sl[i] - slot_lo < span;
-                any |= in[i];
-            }
-            if (!any && !node_out) continue;
-            uint2 inf[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) inf[i] = (in[i] || node_out) ? nv.info[sl[i]] : make_uint2(0u, 0u);
-            if (any) {
-                const uint4 rk = __ldcs(reinterpret_cast<const uint4 *>(win_rank + w));
-                const int4 rd = __ldcs(reinterpret_cast<const int4 *>(win_read + w));
-                if (in[0]) raw[(size_t)inf[0].y + rk.x] = (uint32_t)rd.x;
-                if (in[1]) raw[(size_t)inf[1].y + rk.y] = (uint32_t)rd.y;
-                if (in[2]) raw[(size_t)inf[2].y + rk.z] = (uint32_t)rd.z;
-                if (in[3]) raw[(size_t)inf[3].y + rk.w] = (uint32_t)rd.w;
-            }
-            if (node_out)
-                __stcs(reinterpret_cast<int4 *>(node_out + w), make_int4((int)inf[0].x, (int)inf[1].x, (int)inf[2].x, (int)inf[3].x));
-        } else {
-            for (int i = 0; i < 4 && w + i < W; ++i) {
-                const unsigned int sl = (unsigned int)win_slot[w + i];
-                const uint2 inf = nv.info[sl];
-                if (sl - slot_lo < span) raw[(size_t)inf.y + win_rank[w + i]] = (uint32_t)win_read[w + i];
-                if (node_out) node_out[w + i] = (int)inf.x;
-            }
-        }
-    }
-}
 
 // lazy removal of the equal neighbours the sort left (a gene-mer that occurs twice on one read): unique
 // counts -> offsets (scan), then one warp per node copies its list without them

@@ -226,14 +226,13 @@ __device__ __forceinline__ long long node_find_local(const BuildParams &L, bool 
 // its global node index, the global node its local coverage.  The probed table is the rank's own
 // L2-resident node table -- no table over the (much larger) global node set is ever built.
 __global__ void k_global_to_local(const BuildParams L, int n16, const NodeView nv, const int32_t *__restrict__ node_key,
-                                  long long n_global, uint32_t *__restrict__ cov_local, uint32_t *__restrict__ node_src) {
+                                  long long n_global, uint32_t *__restrict__ cov_local) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_global) return;
     const long long s = node_find_local(L, n16 != 0, node_key + j * L.k);
     if (s < 0) return;
     nv.a((unsigned int)s) = (unsigned int)j;
     cov_local[j] = nv.c((unsigned int)s) + 1u;
-    node_src[j] = nv.base((unsigned int)s);
 }
 
 // merged records -> the same offset in every rank's window (stores over NVLink, 4-byte granularity
