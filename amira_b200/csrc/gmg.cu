@@ -90,7 +90,7 @@ struct amira_gmg {
     // nodes (cur) and compaction targets (alt)
     DevBuf node_key, node_cov, node_dir, node_comp, reads_off, reads;
     DevBuf node_key2, node_cov2, node_dir2, node_comp2, reads_off2, reads2;
-    DevBuf parent, is_root, cc_min;
+    DevBuf parent, is_root, cc_min, link, run_id;  // link: node i is joined to node i - 1; run_id: run of linked nodes
     // edges
     DevBuf e_src, e_tgt, e_sd, e_td, e_cov;
     DevBuf e_src2, e_tgt2, e_sd2, e_td2, e_cov2;
@@ -378,6 +378,8 @@ int reserve_graph(amira_gmg *h, int64_t capN, int64_t capE) {
     AMIRA_TRY(h->node_dir.reserve(capN + 1));
     AMIRA_TRY(h->node_comp.reserve(sizeof(uint32_t) * (capN + 1)));
     AMIRA_TRY(h->parent.reserve(sizeof(int32_t) * (capN + 1)));
+    AMIRA_TRY(h->link.reserve(capN + 2));
+    AMIRA_TRY(h->run_id.reserve(sizeof(int32_t) * (capN + 2)));
     AMIRA_TRY(h->is_root.reserve(sizeof(int) * (capN + 2)));
     AMIRA_TRY(h->cc_min.reserve(sizeof(unsigned int) * (capN + 1)));
     AMIRA_TRY(h->reads_off.reserve(sizeof(int64_t) * (capN + 2)));
@@ -529,7 +531,7 @@ int enqueue_order(amira_gmg *h) {
         Phase ph(h, AMIRA_PH_EMIT_NODES);
         LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->nview, h->ids, h->k, bm_node,
                h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(), h->node_dir.as<int8_t>(),
-               h->parent.as<int32_t>(),
+               h->link.as<uint8_t>(),
                (h->n16 && h->key_bits > 0) ? h->ntab.as<NodeSlot16>() : (const NodeSlot16 *)nullptr, h->key_bits);
     }
     return AMIRA_OK;
@@ -550,16 +552,22 @@ int enqueue_tail(amira_gmg *h) {
         SideStream side(h);
         unsigned long long *deg = h->adj_off.as<unsigned long long>();
         bool counted = false;
+        const int32_t *run_ids = nullptr;
         if (h->world == 1) {
             Phase ph(h, AMIRA_PH_EMIT);
             LAUNCH(h, k_fill_u64, h->n_sm * 4, 256, deg, N, 2, 2, 0ull);
             LAUNCH(h, k_emit_edges, std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16), 256, h->eview, h->nview, bm_ea, bm_eb,
                    h->cnt_edge.as<int>(), N, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
-                   h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), deg, h->d_status.as<int>());
+                   h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), deg, h->link.as<uint8_t>(), h->d_status.as<int>());
             counted = true;
-            // union-find in first-seen edge order rather than table order: measured 0.49 ms against 0.73 ms,
-            // and independent of where the hash happened to put the edges
-            LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(h->cap_edges, 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>());
+            // runs of consecutive first-seen nodes joined by an edge (a prefix count, no pointer chasing), then
+            // union-find over the runs with the edges that leave a run, in first-seen edge order
+            run_ids = h->run_id.as<int32_t>();
+            AMIRA_TRY(run_scan(h, RunLoad{h->link.as<uint8_t>()}, RunStore{h->run_id.as<int32_t>(), h->parent.as<int32_t>(), N},
+                               dsz(h, SZ_NODES), 1, 0, h->cap_nodes));
+            // (a compacted list of the run-leaving edges, every lane busy with a union, was measured SLOWER: 0.38 ms
+            // against 0.19 ms for this in-order scan of the edge arrays with ~4 of 32 lanes in a find)
+            LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(h->cap_edges, 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>(), run_ids);
         } else if (h->sh_Eg > 0) {
             Phase ph(h, AMIRA_PH_EMIT);
             LAUNCH(h, k_emit_edges_sorted, grid_for(h->sh_Eg, 256), 256, h->x_sorti2.as<unsigned int>(), h->sh_gedge,
@@ -571,7 +579,7 @@ int enqueue_tail(amira_gmg *h) {
             Phase ph(h, AMIRA_PH_COMPONENTS);
             LAUNCH(h, k_fill_u32, h->n_sm * 4, 256, h->cc_min.as<uint32_t>(), N, 1, 1, 0xFFFFFFFFu);
             LAUNCH(h, k_cc_flatten, (int)std::min<int64_t>(grid_for(h->cap_nodes, 256), (int64_t)h->n_sm * 64), 256, h->parent.as<int32_t>(), N, h->cc_min.as<unsigned int>(),
-                   h->node_comp.as<uint32_t>());
+                   h->node_comp.as<uint32_t>(), run_ids);
             AMIRA_TRY(run_scan(h, FirstLoad{h->node_comp.as<uint32_t>(), h->cc_min.as<unsigned int>()},
                                FirstStore{h->is_root.as<int>(), N, dsz(h, 0)}, dsz(h, SZ_NODES), 1, 0, h->cap_nodes));
             LAUNCH(h, k_cc_number, (int)std::min<int64_t>(grid_for(h->cap_nodes, 256), (int64_t)h->n_sm * 64), 256, h->cc_min.as<unsigned int>(), h->is_root.as<int>(), N,
@@ -592,8 +600,8 @@ int enqueue_tail(amira_gmg *h) {
                    h->nview, h->reads_off.as<int64_t>(), dsz(h, SZ_NODES), u, h->unit_lo.as<int>(), h->d_status.as<int>());
             unsigned int *bcur = h->bucket_cursor.as<unsigned int>();
             LAUNCH(h, k_bucket_base, INC_NB_MAX / 256, 256, h->unit_lo.as<int>(), h->reads_off.as<int64_t>(), u, bcur + INC_NB_MAX, bcur);
-            const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PART_TILE - 1) / PART_TILE), (int64_t)h->n_sm * 4);
-            k_partition<<<pgrid, PART_THREADS, 0, st>>>(h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(),
+            const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PART_TILE - 1) / PART_TILE), (int64_t)h->n_sm * PART_CTAS_V);
+            k_partition<<<pgrid, PART_THREADS, PART_SMEM, st>>>(h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(),
                                                         h->win_node.as<int32_t>(), (const long long *)h->d_sizes.p, bcur + INC_NB_MAX, u, bcur,
                                                         h->inc_rec.as<uint2>());
             h->launches++;
@@ -1370,6 +1378,7 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     AMIRA_CUDA(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
     AMIRA_CUDA(cudaFuncSetAttribute(k_unit_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INC_SMEM));
+    AMIRA_CUDA(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_SMEM));
     int occ = 1;
     AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_insert_windows<5, true, true>), INS_THREADS, 0));
     h->insert_ctas_per_sm = std::max(1, occ);
@@ -1408,7 +1417,7 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->win_node, &h->win_dir, &h->win_read, &h->win_start, &h->win_end, &h->ntab, &h->etab,
                       &h->bitmaps, &h->cnt_node, &h->cnt_edge, &h->node_key, &h->node_cov, &h->node_dir, &h->node_comp,
                       &h->reads_off, &h->reads, &h->node_key2, &h->node_cov2, &h->node_dir2, &h->node_comp2,
-                      &h->reads_off2, &h->reads2, &h->parent, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
+                      &h->reads_off2, &h->reads2, &h->parent, &h->link, &h->run_id, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
                       &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
                       &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->inc_rec, &h->unit_lo, &h->bucket_cursor, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->dups,
                       &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,

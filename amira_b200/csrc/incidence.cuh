@@ -23,8 +23,8 @@
 //                  coalesced.  Nothing is sorted in global memory, nothing is read twice from DRAM.
 //
 // A unit whose last list is so long that the piece outgrows shared memory (a gene-mer on more than
-// INC_BIG windows) falls back to placing the reads in global memory through per-node cursors and sorting
-// the segments with segsort.cuh (lists above 256 entries go to its work lists).
+// INC_BIG windows) is done in two parts, the last list on its own; a single list above INC_CAPV entries
+// falls back to placing the reads in global memory and sorting them with segsort.cuh (its work lists).
 #pragma once
 
 #include "common.cuh"
@@ -43,9 +43,15 @@ constexpr int INC_BATCH = 8;                 // records a thread has in flight
 constexpr int INC_CUR_WORDS = (INC_S + INC_CAPV / 2) / 2 + 8;  // 16-bit cursors, two to a word
 constexpr size_t INC_SMEM = sizeof(uint32_t) * (INC_CAPV + 4) + sizeof(uint16_t) * (INC_S + 8) + (INC_S + 8) + sizeof(uint32_t) * INC_CUR_WORDS;
 
-constexpr int PART_THREADS = 256;   // small CTAs, five to an SM: each tile is a chain of dependent round trips
+#ifndef PART_THREADS_V
+#define PART_THREADS_V 256
+#define PART_CTAS_V 3
+#endif
+constexpr int PART_THREADS = PART_THREADS_V;   // small CTAs, three to an SM (more do not help: the pass is bound by L2 transactions), which leaves registers for the second stream
 constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = PART_THREADS * PART_ITEMS;
+constexpr int PART_TOUCH = PART_TILE < INC_NB_MAX ? PART_TILE : INC_NB_MAX;
+constexpr size_t PART_SMEM = 2 * sizeof(uint32_t) * INC_NB_MAX + 2 * sizeof(uint16_t) * PART_TOUCH;
 
 struct UnitPlan {
     int g;             // bucket = unit >> g
@@ -95,13 +101,14 @@ __global__ void k_bucket_base(const int *__restrict__ unit_lo, const int64_t *__
 // touched bucket in the bucket's region (one global atomic each), store the records at run start + rank.
 // The slots and reads of the NEXT tile are loaded before the current one is ranked, so the streams never stop
 // while a tile waits for its gathers, its reservations and its barriers.
-__global__ void __launch_bounds__(PART_THREADS, 4)
+__global__ void __launch_bounds__(PART_THREADS, PART_CTAS_V)
 k_partition(const uint2 *__restrict__ info, const int32_t *__restrict__ win_slot, const int32_t *__restrict__ win_read,
             int32_t *__restrict__ win_node, const long long *__restrict__ sizes, const uint32_t *__restrict__ bucket_base,
             const UnitPlan plan, unsigned int *__restrict__ bucket_cursor, uint2 *__restrict__ rec) {
-    __shared__ uint32_t hist[INC_NB_MAX];          // windows of the tile per bucket (zero between tiles)
-    __shared__ uint32_t run0[INC_NB_MAX];          // where the tile's run starts in the record array
-    __shared__ uint16_t touched[2][PART_TILE];     // buckets the tile touched (double-buffered by tile parity)
+    extern __shared__ __align__(16) unsigned char p_smem[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(p_smem);  // windows of the tile per bucket (zero between tiles)
+    uint32_t *run0 = hist + INC_NB_MAX;                     // where the tile's run starts in the record array
+    uint16_t (*touched)[PART_TOUCH] = reinterpret_cast<uint16_t (*)[PART_TOUCH]>(run0 + INC_NB_MAX);  // buckets the tile touched (double-buffered by tile parity)
     __shared__ uint32_t n_touched[2];
     const long long W = sizes[SZ_W];
     const int g = plan.g;
@@ -142,7 +149,7 @@ k_partition(const uint2 *__restrict__ info, const int32_t *__restrict__ win_slot
                 __stcs(win_node + w0 + j, (int32_t)node[i]);
                 const uint32_t r = atomicAdd(&hist[br[i]], 1u);
                 if (r == 0) touched[par][atomicAdd(&n_touched[par], 1u)] = (uint16_t)br[i];
-                br[i] |= r << 12;  // bucket | rank within (tile, bucket)
+                br[i] |= r << 12;  // bucket | rank within (tile, bucket): tiles of at most 2^20 windows
             }
         }
         __syncthreads();
@@ -264,13 +271,20 @@ k_unit_lists(const uint2 *__restrict__ rec, const int *__restrict__ unit_lo, con
     __shared__ uint32_t s_total;
     const int q = blockIdx.x;
     if (q >= plan.n_units) return;
-    const int node_lo = unit_lo[q], node_hi = unit_lo[q + 1];
-    const int nn = node_hi - node_lo;
-    if (nn <= 0) return;
+    const int unit_node_lo = unit_lo[q], unit_node_hi = unit_lo[q + 1];
+    if (unit_node_hi <= unit_node_lo) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t *const roff = J.off;
+    // A unit that outgrows shared memory does so because of its LAST list (the others start inside one INC_C cell):
+    // it is done in two parts, the last list on its own.
+    const bool two_parts = roff[unit_node_hi] - roff[unit_node_lo] > INC_CAPV && unit_node_hi - unit_node_lo > 1;
+  for (int part = 0; part < (two_parts ? 2 : 1); ++part) {
+    const int node_lo = (two_parts && part == 1) ? unit_node_hi - 1 : unit_node_lo;
+    const int node_hi = (two_parts && part == 0) ? unit_node_hi - 1 : unit_node_hi;
+    const int nn = node_hi - node_lo;
     const long long base = roff[node_lo];
     const long long total = roff[node_hi] - base;
+    __syncthreads();  // the previous part is done with shared memory
     // the bucket's region of the record array
     const int b = q >> plan.g;
     const long long rb = roff[unit_lo[b << plan.g]], re = roff[unit_lo[(b + 1) << plan.g]];
@@ -291,7 +305,7 @@ k_unit_lists(const uint2 *__restrict__ rec, const int *__restrict__ unit_lo, con
         }
         __syncthreads();
         segsort_range(J, work, node_lo, node_hi, warp, INC_THREADS / 32, lane);
-        return;
+        continue;
     }
 
     // ---- sub-bucket table: sub_off[i] = first sub-bucket of node i of the unit, shf[i] = read bits dropped to
@@ -490,6 +504,7 @@ k_unit_lists(const uint2 *__restrict__ rec, const int *__restrict__ unit_lo, con
         }
         for (int j = first + 4 * n4 + tid; j < n; j += INC_THREADS) out[j] = vals[j];
     }
+  }
 }
 
 }  // namespace amira

@@ -116,7 +116,7 @@ struct RankStore {
 __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids, int k,
                              const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
                              int32_t *__restrict__ node_key, uint32_t *__restrict__ node_cov,
-                             int8_t *__restrict__ node_dir, int32_t *__restrict__ parent,
+                             int8_t *__restrict__ node_dir, uint8_t *__restrict__ link,
                              const NodeSlot16 *__restrict__ tab16, const int key_bits) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
@@ -128,7 +128,7 @@ __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids,
         nv.a(s) = (unsigned int)idx;
         node_cov[idx] = nv.c(s) + 1u;
         node_dir[idx] = neg ? -1 : 1;
-        parent[idx] = idx;
+        link[idx] = 0;
         if (tab16) {
             // 16-byte slots: the canonical gene-mer is in the slot (top 22 bits in `word`, low 63 in `key`), no need
             // to go back to the ids
@@ -200,7 +200,7 @@ __global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
                              const int *__restrict__ pref_edge, const Cnt n_nodes, int32_t *__restrict__ e_src,
                              int32_t *__restrict__ e_tgt, int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td,
                              uint32_t *__restrict__ e_cov, unsigned long long *__restrict__ deg,
-                             const int *__restrict__ status) {
+                             uint8_t *__restrict__ link, const int *__restrict__ status) {
     if (poisoned(status)) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const long long N = n_nodes.get();
@@ -224,6 +224,10 @@ __global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
             e_cov[idx + 1] = cov;
             atomicAdd(&deg[src + (sd < 0 ? N : 0)], 1ull);
             atomicAdd(&deg[tgt + (-td < 0 ? N : 0)], 1ull);
+            // consecutive first-seen nodes joined by an edge (three quarters of all adjacencies: reads walk paths)
+            // form RUNS; the components pass unites runs, not nodes
+            if (src - tgt == 1) link[src] = 1;
+            else if (tgt - src == 1) link[tgt] = 1;
         } else {
             // S == T: forward and reverse are the same Edge object, incremented twice per pair
             e_src[idx] = src; e_tgt[idx] = src; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = 2u * cov;
@@ -328,29 +332,56 @@ __global__ void k_adj_scatter(const int32_t *__restrict__ e_src, const int8_t *_
 
 // ---- components -------------------------------------------------------------------------------------
 // union-find over the emitted edges in first-seen order (each undirected adjacency once)
+// run_id (nullable): run of every node; parent then spans the runs
 __global__ void k_union_edges(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt, const Cnt n_edges,
-                              int32_t *__restrict__ parent) {
+                              int32_t *__restrict__ parent, const int32_t *__restrict__ run_id) {
     const long long E = n_edges.get();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
         const int s = e_src[e], t = e_tgt[e];
-        if (s < t) uf_union(parent, s, t);
+        if (s >= t) continue;
+        if (run_id) {
+            if (t - s == 1) continue;  // same run by construction
+            const int a = run_id[s], b = run_id[t];
+            if (a != b) uf_union(parent, a, b);
+        } else {
+            uf_union(parent, s, t);
+        }
     }
 }
+
+// runs of consecutive linked nodes: run_id = (number of run starts up to and including the node) - 1
+struct RunLoad {
+    const uint8_t *link;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return link[i] ? 0ull : 1ull; }
+};
+struct RunStore {
+    int32_t *run_id, *parent;
+    Cnt n;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long v) const {
+        if (i >= n.get()) return;
+        const int32_t r = (int32_t)(excl + v) - 1;
+        run_id[i] = r;
+        if (v) parent[r] = r;
+    }
+};
 
 // root of every node (read-only walk: the unions are over, trees are shallow thanks to the random
 // linking) and each component's first node (cmin starts at 0xFFFFFFFF)
 __global__ void k_cc_flatten(const int32_t *__restrict__ parent, const Cnt n_nodes, unsigned int *__restrict__ cmin,
-                             uint32_t *__restrict__ root) {
+                             uint32_t *__restrict__ root, const int32_t *__restrict__ run_id) {
     const long long N = n_nodes.get();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        int r = (int)i;
+        int r = run_id ? run_id[i] : (int)i;
         for (int p = parent[r]; p != r; p = parent[r]) r = p;
         root[i] = (uint32_t)r;
-        // threads run roughly in index order: after the first few updates the minimum is final and the
-        // remaining nodes of a (giant) component skip the atomic
-        if ((unsigned int)i < ((volatile unsigned int *)cmin)[r]) atomicMin(&cmin[r], (unsigned int)i);
+        // one atomic per (warp, component): the lanes of a warp hold ascending node indices, so the lowest lane of
+        // every group carries the group's minimum; threads run roughly in index order, so after the first few
+        // updates the minimum is final and the remaining warps of a (giant) component skip the atomic
+        const unsigned int peers = __match_any_sync(__activemask(), r);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1 && (unsigned int)i < ((volatile unsigned int *)cmin)[r])
+            atomicMin(&cmin[r], (unsigned int)i);
     }
 }
 
