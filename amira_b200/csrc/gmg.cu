@@ -572,7 +572,13 @@ int enqueue_tail(amira_gmg *h) {
             Phase ph(h, AMIRA_PH_EMIT);
             LAUNCH(h, k_emit_edges_sorted, grid_for(h->sh_Eg, 256), 256, h->x_sorti2.as<unsigned int>(), h->sh_gedge,
                    h->x_fan.as<int>(), (long long)h->sh_Eg, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(),
-                   h->e_sd.as<int8_t>(), h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->parent.as<int32_t>());
+                   h->e_sd.as<int8_t>(), h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), h->link.as<uint8_t>());
+        }
+        if (h->world > 1) {
+            run_ids = h->run_id.as<int32_t>();
+            AMIRA_TRY(run_scan(h, RunLoad{h->link.as<uint8_t>()}, RunStore{h->run_id.as<int32_t>(), h->parent.as<int32_t>(), N},
+                               dsz(h, SZ_NODES), 1, 0, h->cap_nodes));
+            LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(std::max<int64_t>(h->cap_edges, 1), 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>(), run_ids);
         }
         AMIRA_TRY(build_adjacency(h, counted));
         {
@@ -1123,8 +1129,6 @@ int sharded_merge(amira_gmg *h) {
         r_meta = h->x_rmeta.as<NodeRec>();
     }
     tr.mark("n_a2a");
-    AMIRA_TRY(h->x_rkey2.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
-    AMIRA_TRY(h->x_rmeta2.reserve(sizeof(NodeRec) * std::max<int64_t>(Nr, 1)));
 
     // ---- owner merge: records in first-position order into a table (sum of counts, earliest record)
     const int64_t sort_cap = std::max<int64_t>(Nr, 1);
@@ -1142,18 +1146,16 @@ int sharded_merge(amira_gmg *h) {
     memset(&P, 0, sizeof(P));
     P.k = k;
     P.status = h->d_status.as<int>();
+    // earliest first occurrence per merged gene-mer (x_rmeta2 doubles as that array)
+    AMIRA_TRY(h->x_rmeta2.reserve(sizeof(unsigned long long) * (size_t)mcap));
+    AMIRA_CUDA(cudaMemsetAsync(h->x_rmeta2.p, 0xFF, sizeof(unsigned long long) * (size_t)mcap, st));
     if (Nr > 0) {
-        LAUNCH(h, k_rec_ord_keys, grid_for(Nr, 256), 256, r_meta, (long long)Nr, h->x_sortk.as<unsigned long long>(),
-               h->x_sorti.as<unsigned int>());
-        AMIRA_TRY(sort_by_ord(h, Nr));
-        LAUNCH(h, k_gather_node_recs, grid_for(Nr, 256), 256, h->x_sorti2.as<unsigned int>(), r_key, r_meta, k,
-               (long long)Nr, h->x_rkey2.as<int32_t>(), h->x_rmeta2.as<NodeRec>());
-        P.ids = h->x_rkey2.as<int32_t>();
+        P.ids = r_key;
         P.ntab = h->x_tab.as<NodeSlot>();
         P.ncap = (unsigned int)mcap;
-        LAUNCH(h, k_insert_records, grid_for(Nr, 256), 256, P, (long long)Nr, h->x_rmeta2.as<NodeRec>());
+        LAUNCH(h, k_insert_records, grid_for(Nr, 256), 256, P, (long long)Nr, r_meta, h->x_rmeta2.as<unsigned long long>());
         LAUNCH(h, k_pack_merged_nodes, std::min<int>(grid_for(mcap, 256), h->n_sm * 16), 256, h->x_tab.as<NodeSlot>(),
-               (unsigned int)mcap, h->x_rkey2.as<int32_t>(), h->x_rmeta2.as<NodeRec>(), k, d_cnt, h->x_mkey.as<int32_t>(),
+               (unsigned int)mcap, r_key, h->x_rmeta2.as<unsigned long long>(), k, d_cnt, h->x_mkey.as<int32_t>(),
                h->x_mmeta.as<NodeRec>());
     }
     AMIRA_TRY(gather_counts(h, g_off));
@@ -1194,7 +1196,7 @@ int sharded_merge(amira_gmg *h) {
                h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
         AMIRA_TRY(sort_by_ord(h, Ng));
         LAUNCH(h, k_finalize_nodes, grid_for(Ng, 256), 256, h->x_sorti2.as<unsigned int>(), g_key, g_meta, k, (long long)Ng, h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
-               h->node_dir.as<int8_t>(), h->parent.as<int32_t>());
+               h->node_dir.as<int8_t>(), h->link.as<uint8_t>());
         // local slots -> global node indices: probe the rank's own node table with every global gene-mer
         if (h->G > 0)
             LAUNCH(h, k_global_to_local, grid_for(Ng, 256), 256, h->local_P, h->n16 ? 1 : 0, h->nview,

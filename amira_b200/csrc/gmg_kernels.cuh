@@ -37,7 +37,7 @@ constexpr int WC = 128;        // calls per warp chunk
 constexpr int INS_TILE = WC;   // granularity of the chunk -> first read map
 constexpr int MAX_K = 64;
 #ifndef AMIRA_INS_MINB
-#define AMIRA_INS_MINB 8
+#define AMIRA_INS_MINB 6
 #endif
 constexpr int NR_STAGE = 30;   // reads of a chunk whose offsets are staged in shared memory
 constexpr unsigned int INVALID_VAL = 0xFFFFFFFFu;
@@ -305,6 +305,46 @@ __device__ __forceinline__ unsigned int node_insert16(const BuildParams &P, cons
     return 0;
 }
 
+// one bucket of the edge table against `key`: true when the pair event has been counted (found or claimed)
+__device__ __forceinline__ bool edge_bucket16(EdgeSlot16 *B, unsigned long long key, unsigned int ord, unsigned long long c0,
+                                              unsigned long long o0, unsigned long long c1, unsigned long long o1) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        unsigned long long cur = i ? c1 : c0;
+        unsigned int cord = (unsigned int)((i ? o1 : o0) >> 32);
+        if (cur == EMPTY64) {
+            unsigned long long old = atomicCAS(&B[i].key, EMPTY64, key);
+            cur = (old == EMPTY64) ? key : old;
+            cord = 0xFFFFFFFFu;
+        }
+        if (cur == key) {
+            if (ord < cord) atomicMin(&B[i].ord, ord);
+            atomicAdd(&B[i].cov, 1u);
+            return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ unsigned int edge_bucket_of(const BuildParams &P, unsigned long long key) {
+    return (unsigned int)(((unsigned long long)edge_hash32(key) * (P.ecap >> 1)) >> 32);
+}
+
+// probe sequence from bucket b on (b itself included)
+__device__ __forceinline__ void edge_insert16_from(const BuildParams &P, unsigned long long key, unsigned int ord, unsigned int b) {
+    const unsigned int nb = P.ecap >> 1;
+    const unsigned int max_probe = min(MAX_PROBES, nb);
+    for (unsigned int probe = 0; probe < max_probe; ++probe) {
+        if (b >= nb) b = 0;
+        EdgeSlot16 *B = P.etab16 + 2 * (size_t)b;
+        unsigned long long c0, o0, c1, o1;
+        load_bucket(B, c0, o0, c1, o1);
+        if (edge_bucket16(B, key, ord, c0, o0, c1, o1)) return;
+        ++b;
+    }
+    P.status[ST_OVERFLOW_E] = 1;
+}
+
 __device__ __forceinline__ void edge_insert16(const BuildParams &P, unsigned long long key, unsigned int ord) {
     const unsigned int nb = P.ecap >> 1;
     unsigned int b = (unsigned int)(((unsigned long long)edge_hash32(key) * nb) >> 32);
@@ -517,21 +557,49 @@ __global__ void __launch_bounds__(INS_THREADS, AMIRA_INS_MINB) k_insert_windows(
         }
         __syncwarp();
         // ---- adjacent pairs of the same read
+#define AMIRA_PAIR(pl_, valid_, key_, ord_)                                                                              \
+    {                                                                                                                    \
+        valid_ = false;                                                                                                  \
+        key_ = 0;                                                                                                        \
+        ord_ = 0;                                                                                                        \
+        if ((pl_) + 1 < len) {                                                                                           \
+            const unsigned int a_ = S.val[pl_], b_ = S.val[(pl_) + 1];                                                   \
+            if (a_ != INVALID_VAL && b_ != INVALID_VAL && S.j[(pl_) + 1] == S.j[pl_]) {                                  \
+                const unsigned int sa_ = a_ & 0x7FFFFFFFu, sb_ = b_ & 0x7FFFFFFFu;                                       \
+                const unsigned int sdn_ = a_ >> 31, tdn_ = b_ >> 31;                                                     \
+                key_ = ((unsigned long long)min(sa_, sb_) << 32) | ((unsigned long long)max(sa_, sb_) << 1) |            \
+                       (unsigned long long)(sdn_ == tdn_);                                                               \
+                ord_ = ((unsigned long long)(c0 + (pl_)) << 2) | ((unsigned long long)(sa_ > sb_) << 1) | sdn_;           \
+                valid_ = true;                                                                                           \
+            }                                                                                                            \
+        }                                                                                                                \
+    }
+        if (E16) {
+            // two pairs per lane in flight: both bucket loads are issued before either is looked at
 #pragma unroll 1
-        for (int pl = lane; pl + 1 < len; pl += 32) {
-            const unsigned int a = S.val[pl], b = S.val[pl + 1];
-            if (a == INVALID_VAL || b == INVALID_VAL) continue;
-            if (S.j[pl + 1] != S.j[pl]) continue;
-            const unsigned int sa = a & 0x7FFFFFFFu, sb = b & 0x7FFFFFFFu;
-            const unsigned int sdneg = a >> 31, tdneg = b >> 31;
-            const unsigned int lo = min(sa, sb), hi = max(sa, sb);
-            const unsigned long long key =
-                ((unsigned long long)lo << 32) | ((unsigned long long)hi << 1) | (unsigned long long)(sdneg == tdneg);
-            const unsigned long long ord =
-                ((unsigned long long)(c0 + pl) << 2) | ((unsigned long long)(sa > sb) << 1) | sdneg;
-            if (E16) edge_insert16(P, key, (unsigned int)ord);
-            else edge_insert(P, key, ord);
+            for (int pl = lane; pl + 1 < len; pl += 64) {
+                bool v0, v1;
+                unsigned long long k0, k1, r0, r1;
+                AMIRA_PAIR(pl, v0, k0, r0);
+                AMIRA_PAIR(pl + 32, v1, k1, r1);
+                const unsigned int b0 = edge_bucket_of(P, k0), b1 = edge_bucket_of(P, k1);
+                EdgeSlot16 *B0 = P.etab16 + 2 * (size_t)b0, *B1 = P.etab16 + 2 * (size_t)b1;
+                unsigned long long x0 = 0, y0 = 0, x1 = 0, y1 = 0, u0 = 0, w0 = 0, u1 = 0, w1 = 0;
+                if (v0) load_bucket(B0, x0, y0, x1, y1);
+                if (v1) load_bucket(B1, u0, w0, u1, w1);
+                if (v0 && !edge_bucket16(B0, k0, (unsigned int)r0, x0, y0, x1, y1)) edge_insert16_from(P, k0, (unsigned int)r0, b0 + 1);
+                if (v1 && !edge_bucket16(B1, k1, (unsigned int)r1, u0, w0, u1, w1)) edge_insert16_from(P, k1, (unsigned int)r1, b1 + 1);
+            }
+        } else {
+#pragma unroll 1
+            for (int pl = lane; pl + 1 < len; pl += 32) {
+                bool v0;
+                unsigned long long k0, r0;
+                AMIRA_PAIR(pl, v0, k0, r0);
+                if (v0) edge_insert(P, k0, r0);
+            }
         }
+#undef AMIRA_PAIR
         __syncwarp();
     }
 }

@@ -128,20 +128,26 @@ __global__ void k_gather_node_recs(const unsigned int *__restrict__ perm, const 
     out_meta[i] = in_meta[s];
 }
 
-// records (canonical keys, k ids each, sorted by first position) -> table; the slot keeps the
-// smallest record index (= earliest first position) and the weighted count
-__global__ void k_insert_records(const BuildParams P, long long n, const NodeRec *__restrict__ meta) {
+// records (canonical keys, k ids each, in the order they arrived) -> table; the slot names one record of the
+// gene-mer (whichever: it only serves key comparisons) and collects the weighted count and, in ord_min, the
+// earliest first occurrence (position << 1 | direction) -- no sort of the received records is needed
+__global__ void k_insert_records(const BuildParams P, long long n, const NodeRec *__restrict__ meta,
+                                 unsigned long long *__restrict__ ord_min) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int32_t *win = P.ids + r * P.k;
     const unsigned long long h = canonical_hash(win, P.k, 0);
     const unsigned long long mine = ((h >> FP_SHIFT) << FP_SHIFT) | ((unsigned long long)(r * P.k) << 1);
     const unsigned int slot = node_insert(P, win, 0, false, 0ull, 0ull, h, mine);
-    if (meta) atomicAdd(&P.ntab[slot].cov, meta[r].cov);
+    if (meta) {
+        atomicAdd(&P.ntab[slot].cov, meta[r].cov);
+        const unsigned long long o = meta[r].ord;
+        if (o < ((volatile unsigned long long *)ord_min)[slot]) atomicMin(&ord_min[slot], o);
+    }
 }
 
 __global__ void k_pack_merged_nodes(const NodeSlot *__restrict__ tab, unsigned int cap, const int32_t *__restrict__ keys,
-                                    const NodeRec *__restrict__ meta, int k, unsigned long long *__restrict__ counter,
+                                    const unsigned long long *__restrict__ ord_min, int k, unsigned long long *__restrict__ counter,
                                     int32_t *__restrict__ out_key, NodeRec *__restrict__ out_meta) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride) {
@@ -151,7 +157,7 @@ __global__ void k_pack_merged_nodes(const NodeSlot *__restrict__ tab, unsigned i
         const long long i = reserve_one(counter);
         for (int j = 0; j < k; ++j) out_key[i * k + j] = keys[r * k + j];
         NodeRec o;
-        o.ord = meta[r].ord;
+        o.ord = ord_min[s];
         o.cov = tab[s].cov + 1u;   // counts from 0xFFFFFFFF: the sum of the merged weights
         o.pad = 0;
         out_meta[i] = o;
@@ -161,14 +167,14 @@ __global__ void k_pack_merged_nodes(const NodeSlot *__restrict__ tab, unsigned i
 __global__ void k_finalize_nodes(const unsigned int *__restrict__ perm, const int32_t *__restrict__ g_key,
                                  const NodeRec *__restrict__ g_meta, int k, long long n, int32_t *__restrict__ node_key,
                                  uint32_t *__restrict__ node_cov, int8_t *__restrict__ node_dir,
-                                 int32_t *__restrict__ parent) {
+                                 uint8_t *__restrict__ link) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long s = perm[i];
     for (int j = 0; j < k; ++j) node_key[i * k + j] = g_key[s * k + j];
     node_cov[i] = g_meta[s].cov;
     node_dir[i] = (g_meta[s].ord & 1ull) ? -1 : 1;
-    parent[i] = (int32_t)i;
+    link[i] = 0;
 }
 
 // find-only probe of the LOCAL node table (any layout) for a canonical key; -1 if this rank never saw it.
@@ -349,7 +355,7 @@ struct FanStore {
 __global__ void k_emit_edges_sorted(const unsigned int *__restrict__ perm, const EdgeSlot *__restrict__ recs,
                                     const int *__restrict__ pref, long long n, int32_t *__restrict__ e_src,
                                     int32_t *__restrict__ e_tgt, int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td,
-                                    uint32_t *__restrict__ e_cov, int32_t *__restrict__ parent) {
+                                    uint32_t *__restrict__ e_cov, uint8_t *__restrict__ link) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const EdgeSlot e = recs[perm[i]];
@@ -363,7 +369,9 @@ __global__ void k_emit_edges_sorted(const unsigned int *__restrict__ perm, const
         e_src[idx] = src; e_tgt[idx] = tgt; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = e.cov;
         e_src[idx + 1] = tgt; e_tgt[idx + 1] = src; e_sd[idx + 1] = (int8_t)-td; e_td[idx + 1] = (int8_t)-sd;
         e_cov[idx + 1] = e.cov;
-        uf_union(parent, src, tgt);
+        // consecutive nodes joined by an edge form runs; the components pass unites runs (post_kernels.cuh)
+        if (src - tgt == 1) link[src] = 1;
+        else if (tgt - src == 1) link[tgt] = 1;
     } else {
         e_src[idx] = src; e_tgt[idx] = src; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = 2u * e.cov;
     }
