@@ -529,9 +529,12 @@ int enqueue_order(amira_gmg *h) {
     AMIRA_TRY(enqueue_report(h, 0));
     {
         Phase ph(h, AMIRA_PH_EMIT_NODES);
-        LAUNCH(h, k_emit_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->nview, h->ids, h->k, bm_node,
-               h->cnt_node.as<int>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(), h->node_dir.as<int8_t>(),
-               h->link.as<uint8_t>(),
+        // (node -> slot lives in is_root, which the components pass only needs later)
+        LAUNCH(h, k_rank_nodes, std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16), 256, h->nview, bm_node, h->cnt_node.as<int>(),
+               h->is_root.as<uint32_t>());
+        LAUNCH(h, k_emit_nodes, (int)std::min<int64_t>(grid_for(h->cap_nodes, 256), (int64_t)h->n_sm * 16), 256, h->nview, h->ids, h->k,
+               dcnt(h, SZ_NODES), h->is_root.as<uint32_t>(), h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
+               h->node_dir.as<int8_t>(), h->link.as<uint8_t>(),
                (h->n16 && h->key_bits > 0) ? h->ntab.as<NodeSlot16>() : (const NodeSlot16 *)nullptr, h->key_bits);
     }
     return AMIRA_OK;
@@ -556,17 +559,21 @@ int enqueue_tail(amira_gmg *h) {
         if (h->world == 1) {
             Phase ph(h, AMIRA_PH_EMIT);
             LAUNCH(h, k_fill_u64, h->n_sm * 4, 256, deg, N, 2, 2, 0ull);
-            LAUNCH(h, k_emit_edges, std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16), 256, h->eview, h->nview, bm_ea, bm_eb,
-                   h->cnt_edge.as<int>(), N, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
-                   h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), deg, h->link.as<uint8_t>(), h->d_status.as<int>());
+            // (directed edge -> table entry lives in adj_tmp, which the adjacency pass only needs later)
+            LAUNCH(h, k_rank_edges, std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16), 256, h->eview, bm_ea, bm_eb,
+                   h->cnt_edge.as<int>(), h->adj_tmp.as<uint32_t>(), h->d_status.as<int>());
+            LAUNCH(h, k_emit_edges, (int)std::min<int64_t>(grid_for(h->cap_edges, 256), (int64_t)h->n_sm * 16), 256, h->eview, h->nview,
+                   h->adj_tmp.as<uint32_t>(), E, N, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), h->e_sd.as<int8_t>(),
+                   h->e_td.as<int8_t>(), h->e_cov.as<uint32_t>(), deg, h->link.as<uint8_t>());
             counted = true;
             // runs of consecutive first-seen nodes joined by an edge (a prefix count, no pointer chasing), then
             // union-find over the runs with the edges that leave a run, in first-seen edge order
             run_ids = h->run_id.as<int32_t>();
             AMIRA_TRY(run_scan(h, RunLoad{h->link.as<uint8_t>()}, RunStore{h->run_id.as<int32_t>(), h->parent.as<int32_t>(), N},
                                dsz(h, SZ_NODES), 1, 0, h->cap_nodes));
-            // (a compacted list of the run-leaving edges, every lane busy with a union, was measured SLOWER: 0.38 ms
-            // against 0.19 ms for this in-order scan of the edge arrays with ~4 of 32 lanes in a find)
+            // (measured SLOWER than this in-order scan of the edge arrays with ~4 of 32 lanes in a find, 0.19 ms: a compacted
+            // list of the run-leaving edges with every lane busy, 0.38 ms; hanging every run under its smallest
+            // neighbour run + pointer jumping first, 0.27 ms with hashed linking and 0.51 ms with linking by index)
             LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(h->cap_edges, 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>(), run_ids);
         } else if (h->sh_Eg > 0) {
             Phase ph(h, AMIRA_PH_EMIT);

@@ -112,20 +112,35 @@ struct RankStore {
     }
 };
 
-// node arrays in first-seen order; node_cov[idx] = windows counted by the insert kernel
-__global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids, int k,
-                             const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
-                             int32_t *__restrict__ node_key, uint32_t *__restrict__ node_cov,
-                             int8_t *__restrict__ node_dir, uint8_t *__restrict__ link,
-                             const NodeSlot16 *__restrict__ tab16, const int key_bits) {
+// Node arrays in first-seen order, in two steps so that nothing is written scattered (a 4-byte store to a random
+// place of a fresh array costs a 32-byte sector fill and a write-back): k_rank_nodes gives every occupied slot
+// its rank and records the inverse (node -> slot, one L2-resident array); k_emit_nodes then runs over the NODES
+// in order, gathers the slot and writes every array coalesced.
+__global__ void k_rank_nodes(const NodeView nv, const unsigned int *__restrict__ bm_node, const int *__restrict__ pref_node,
+                             uint32_t *__restrict__ node_slot) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < nv.cap; s += stride) {
-        unsigned long long w = nv.w(s);
+        const unsigned long long w = nv.w(s);
         if (w == EMPTY64) continue;
         const unsigned long long p = (w >> 1) & P_MASK;
-        const int neg = (int)(w & 1ull);
         const int idx = pref_node[p >> 5] + __popc(bm_node[p >> 5] & ((1u << (p & 31)) - 1u));
         nv.a(s) = (unsigned int)idx;
+        node_slot[idx] = s;
+    }
+}
+
+// node_cov[idx] = windows counted by the insert kernel
+__global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids, int k, const Cnt n_nodes,
+                             const uint32_t *__restrict__ node_slot, int32_t *__restrict__ node_key,
+                             uint32_t *__restrict__ node_cov, int8_t *__restrict__ node_dir, uint8_t *__restrict__ link,
+                             const NodeSlot16 *__restrict__ tab16, const int key_bits) {
+    const long long N = n_nodes.get();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < N; idx += stride) {
+        const unsigned int s = node_slot[idx];
+        const unsigned long long w = nv.w(s);
+        const unsigned long long p = (w >> 1) & P_MASK;
+        const int neg = (int)(w & 1ull);
         node_cov[idx] = nv.c(s) + 1u;
         node_dir[idx] = neg ? -1 : 1;
         link[idx] = 0;
@@ -142,11 +157,11 @@ __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids,
                 if (sh >= 64) f = khi >> (sh - 64);
                 else if (sh == 0) f = klo;
                 else f = (klo >> sh) | (khi << (64 - sh));
-                node_key[(int64_t)idx * k + j] = (int)(f & mask) - bias;
+                node_key[idx * k + j] = (int)(f & mask) - bias;
             }
         } else {
             for (int j = 0; j < k; ++j)
-                node_key[(int64_t)idx * k + j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
+                node_key[idx * k + j] = neg ? -ids[p + (k - 1 - j)] : ids[p + j];
         }
     }
 }
@@ -192,18 +207,16 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
     }
 }
 
-// edge arrays in first-seen order: each undirected table entry expands to upstream's forward edge
-// S->T and reverse edge T->S (-td, -sd), or to one self edge counted twice (construct_graph.py:246-277);
-// the adjacency degree of the source side of every directed edge is counted on the way
-__global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
-                             const unsigned int *__restrict__ bm_ea, const unsigned int *__restrict__ bm_eb,
-                             const int *__restrict__ pref_edge, const Cnt n_nodes, int32_t *__restrict__ e_src,
-                             int32_t *__restrict__ e_tgt, int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td,
-                             uint32_t *__restrict__ e_cov, unsigned long long *__restrict__ deg,
-                             uint8_t *__restrict__ link, const int *__restrict__ status) {
+// Edge arrays in first-seen order: each undirected table entry expands to upstream's forward edge S->T and
+// reverse edge T->S (-td, -sd), or to one self edge counted twice (construct_graph.py:246-277).  As for the
+// nodes, k_rank_edges first records which table entry every DIRECTED edge comes from (bit 31: the reverse edge),
+// then k_emit_edges runs over the directed edges in order and writes coalesced; the adjacency degree of the
+// source side of every directed edge is counted on the way.
+constexpr uint32_t EDGE_REV = 0x80000000u;
+__global__ void k_rank_edges(const EdgeView ev, const unsigned int *__restrict__ bm_ea, const unsigned int *__restrict__ bm_eb,
+                             const int *__restrict__ pref_edge, uint32_t *__restrict__ edge_slot, const int *__restrict__ status) {
     if (poisoned(status)) return;
     const unsigned int stride = gridDim.x * blockDim.x;
-    const long long N = n_nodes.get();
     for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < ev.cap; s += stride) {
         unsigned long long key, ord;
         unsigned int ecov;
@@ -212,26 +225,43 @@ __global__ void k_emit_edges(const EdgeView ev, const NodeView nv,
         const unsigned int below = (1u << (p & 31)) - 1u;
         const int idx = pref_edge[p >> 5] + __popc(bm_ea[p >> 5] & below) + __popc(bm_eb[p >> 5] & below);
         const unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
+        edge_slot[idx] = s;
+        if (lo != hi) edge_slot[idx + 1] = s | EDGE_REV;
+    }
+}
+
+__global__ void k_emit_edges(const EdgeView ev, const NodeView nv, const uint32_t *__restrict__ edge_slot, const Cnt n_edges,
+                             const Cnt n_nodes, int32_t *__restrict__ e_src, int32_t *__restrict__ e_tgt,
+                             int8_t *__restrict__ e_sd, int8_t *__restrict__ e_td, uint32_t *__restrict__ e_cov,
+                             unsigned long long *__restrict__ deg, uint8_t *__restrict__ link) {
+    const long long E = n_edges.get(), N = n_nodes.get();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < E; idx += stride) {
+        const uint32_t v = edge_slot[idx];
+        const bool rev = (v & EDGE_REV) != 0;
+        unsigned long long key, ord;
+        unsigned int ecov;
+        ev.get(v & ~EDGE_REV, key, ord, ecov);
+        const unsigned int lo = (unsigned int)(key >> 32), hi = (unsigned int)((key & 0xFFFFFFFFull) >> 1);
         const int rel = (key & 1ull) ? 1 : -1;
         const bool src_hi = (ord >> 1) & 1ull;
-        const int src = (int)nv.a(src_hi ? hi : lo), tgt = (int)nv.a(src_hi ? lo : hi);
-        const int sd = (ord & 1ull) ? -1 : 1, td = rel * sd;
-        const uint32_t cov = ecov + 1u;
-        if (lo != hi) {
-            // forward edge S->T, then the reverse edge T->S with directions (-td, -sd)
-            e_src[idx] = src; e_tgt[idx] = tgt; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = cov;
-            e_src[idx + 1] = tgt; e_tgt[idx + 1] = src; e_sd[idx + 1] = (int8_t)-td; e_td[idx + 1] = (int8_t)-sd;
-            e_cov[idx + 1] = cov;
-            atomicAdd(&deg[src + (sd < 0 ? N : 0)], 1ull);
-            atomicAdd(&deg[tgt + (-td < 0 ? N : 0)], 1ull);
-            // consecutive first-seen nodes joined by an edge (three quarters of all adjacencies: reads walk paths)
-            // form RUNS; the components pass unites runs, not nodes
+        const int fsrc = (int)nv.a(src_hi ? hi : lo), ftgt = (int)nv.a(src_hi ? lo : hi);
+        const int fsd = (ord & 1ull) ? -1 : 1, ftd = rel * fsd;
+        // forward edge S->T, or the reverse edge T->S with directions (-td, -sd); S == T: forward and reverse are
+        // the same Edge object, incremented twice per pair
+        const int src = rev ? ftgt : fsrc, tgt = rev ? fsrc : ftgt;
+        const int sd = rev ? -ftd : fsd, td = rev ? -fsd : ftd;
+        e_src[idx] = src;
+        e_tgt[idx] = tgt;
+        e_sd[idx] = (int8_t)sd;
+        e_td[idx] = (int8_t)td;
+        e_cov[idx] = lo != hi ? ecov + 1u : 2u * (ecov + 1u);
+        atomicAdd(&deg[src + (sd < 0 ? N : 0)], 1ull);
+        // consecutive first-seen nodes joined by an edge (three quarters of all adjacencies: reads walk paths)
+        // form RUNS; the components pass unites runs, not nodes
+        if (!rev) {
             if (src - tgt == 1) link[src] = 1;
             else if (tgt - src == 1) link[tgt] = 1;
-        } else {
-            // S == T: forward and reverse are the same Edge object, incremented twice per pair
-            e_src[idx] = src; e_tgt[idx] = src; e_sd[idx] = (int8_t)sd; e_td[idx] = (int8_t)td; e_cov[idx] = 2u * cov;
-            atomicAdd(&deg[src + (sd < 0 ? N : 0)], 1ull);
         }
     }
 }
