@@ -90,7 +90,7 @@ struct amira_gmg {
     // nodes (cur) and compaction targets (alt)
     DevBuf node_key, node_cov, node_dir, node_comp, reads_off, reads;
     DevBuf node_key2, node_cov2, node_dir2, node_comp2, reads_off2, reads2;
-    DevBuf parent, is_root, cc_min, link, run_id;  // link: node i is joined to node i - 1; run_id: run of linked nodes
+    DevBuf parent, is_root, cc_min, link, run_id, run_pairs;  // link: node i is joined to node i - 1; run_id: run of linked nodes
     // edges
     DevBuf e_src, e_tgt, e_sd, e_td, e_cov;
     DevBuf e_src2, e_tgt2, e_sd2, e_td2, e_cov2;
@@ -379,6 +379,7 @@ int reserve_graph(amira_gmg *h, int64_t capN, int64_t capE) {
     AMIRA_TRY(h->node_comp.reserve(sizeof(uint32_t) * (capN + 1)));
     AMIRA_TRY(h->parent.reserve(sizeof(int32_t) * (capN + 1)));
     AMIRA_TRY(h->link.reserve(capN + 2));
+    if (h->prev_nodes > 0 && h->prev_nodes <= UF_SMALL_RUNS) AMIRA_TRY(h->run_pairs.reserve(sizeof(unsigned long long) * (size_t)(capE / 2 + 4)));
     AMIRA_TRY(h->run_id.reserve(sizeof(int32_t) * (capN + 2)));
     AMIRA_TRY(h->is_root.reserve(sizeof(int) * (capN + 2)));
     AMIRA_TRY(h->cc_min.reserve(sizeof(unsigned int) * (capN + 1)));
@@ -574,7 +575,21 @@ int enqueue_tail(amira_gmg *h) {
             // (measured SLOWER than this in-order scan of the edge arrays with ~4 of 32 lanes in a find, 0.19 ms: a compacted
             // list of the run-leaving edges with every lane busy, 0.38 ms; hanging every run under its smallest
             // neighbour run + pointer jumping first, 0.27 ms with hashed linking and 0.51 ms with linking by index)
-            LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(h->cap_edges, 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>(), run_ids);
+            const unsigned long long *done = nullptr;
+            if (h->prev_nodes > 0 && h->prev_nodes <= UF_SMALL_RUNS) {
+                // small graph (by the previous build on this handle; the kernels check the real run count): unions at
+                // shared-memory latency.  pairs[0] = list length, pairs[1] = done flag, then the list.
+                unsigned long long *pairs = h->run_pairs.as<unsigned long long>();
+                AMIRA_CUDA(cudaMemsetAsync(pairs, 0, 2 * sizeof(unsigned long long), h->cur));
+                h->lib_launches++;
+                LAUNCH(h, k_collect_run_edges, (int)std::min<int64_t>(grid_for(h->cap_edges, 256), (int64_t)h->n_sm * 16), 256, h->e_src.as<int32_t>(),
+                       h->e_tgt.as<int32_t>(), E, N, run_ids, pairs + 2, pairs);
+                k_union_small<<<1, UF_SMALL_THREADS, sizeof(int32_t) * UF_SMALL_RUNS, h->cur>>>(pairs + 2, pairs, N, run_ids, h->parent.as<int32_t>(), pairs + 1);
+                h->launches++;
+                AMIRA_CUDA(cudaGetLastError());
+                done = pairs + 1;
+            }
+            LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(h->cap_edges, 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>(), run_ids, done);
         } else if (h->sh_Eg > 0) {
             Phase ph(h, AMIRA_PH_EMIT);
             LAUNCH(h, k_emit_edges_sorted, grid_for(h->sh_Eg, 256), 256, h->x_sorti2.as<unsigned int>(), h->sh_gedge,
@@ -585,7 +600,7 @@ int enqueue_tail(amira_gmg *h) {
             run_ids = h->run_id.as<int32_t>();
             AMIRA_TRY(run_scan(h, RunLoad{h->link.as<uint8_t>()}, RunStore{h->run_id.as<int32_t>(), h->parent.as<int32_t>(), N},
                                dsz(h, SZ_NODES), 1, 0, h->cap_nodes));
-            LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(std::max<int64_t>(h->cap_edges, 1), 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>(), run_ids);
+            LAUNCH(h, k_union_edges, (int)std::min<int64_t>(grid_for(std::max<int64_t>(h->cap_edges, 1), 256), (int64_t)h->n_sm * 64), 256, h->e_src.as<int32_t>(), h->e_tgt.as<int32_t>(), E, h->parent.as<int32_t>(), run_ids, nullptr);
         }
         AMIRA_TRY(build_adjacency(h, counted));
         {
@@ -1374,7 +1389,8 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
         // between the waves of the bandwidth-bound sort on the main stream
         int prio_lo = 0, prio_hi = 0;
         AMIRA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        AMIRA_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi));
+        const bool side_low = getenv("AMIRA_SIDE_LOW") != nullptr;  // developer experiments
+        AMIRA_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, side_low ? prio_lo : prio_hi));
     }
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     AMIRA_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -1387,6 +1403,7 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     AMIRA_CUDA(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
     AMIRA_CUDA(cudaFuncSetAttribute(k_unit_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INC_SMEM));
+    AMIRA_CUDA(cudaFuncSetAttribute(k_union_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int32_t) * UF_SMALL_RUNS)));
     AMIRA_CUDA(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_SMEM));
     int occ = 1;
     AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_insert_windows<5, true, true>), INS_THREADS, 0));
@@ -1426,7 +1443,7 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->win_node, &h->win_dir, &h->win_read, &h->win_start, &h->win_end, &h->ntab, &h->etab,
                       &h->bitmaps, &h->cnt_node, &h->cnt_edge, &h->node_key, &h->node_cov, &h->node_dir, &h->node_comp,
                       &h->reads_off, &h->reads, &h->node_key2, &h->node_cov2, &h->node_dir2, &h->node_comp2,
-                      &h->reads_off2, &h->reads2, &h->parent, &h->link, &h->run_id, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
+                      &h->reads_off2, &h->reads2, &h->parent, &h->link, &h->run_id, &h->run_pairs, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
                       &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
                       &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->inc_rec, &h->unit_lo, &h->bucket_cursor, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->dups,
                       &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,

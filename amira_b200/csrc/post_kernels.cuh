@@ -168,13 +168,15 @@ __global__ void k_emit_nodes(const NodeView nv, const int32_t *__restrict__ ids,
 
 // ---- union-find -----------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(int32_t *parent, int x) {
-    // path halving; races only ever replace a parent by one of its ancestors
+    // path halving (every other node on the way is re-hung under its grandparent, and the walk moves on to the
+    // grandparent: one level per load); races only ever replace a parent by one of its ancestors
     while (true) {
-        int p = ((volatile int32_t *)parent)[x];
+        const int p = ((volatile int32_t *)parent)[x];
         if (p == x) return x;
-        int gp = ((volatile int32_t *)parent)[p];
-        if (gp != p) parent[x] = gp;
-        x = p;
+        const int gp = ((volatile int32_t *)parent)[p];
+        if (gp == p) return p;
+        parent[x] = gp;
+        x = gp;
     }
 }
 
@@ -362,9 +364,12 @@ __global__ void k_adj_scatter(const int32_t *__restrict__ e_src, const int8_t *_
 
 // ---- components -------------------------------------------------------------------------------------
 // union-find over the emitted edges in first-seen order (each undirected adjacency once)
-// run_id (nullable): run of every node; parent then spans the runs
+// run_id (nullable): run of every node; parent then spans the runs.  done (nullable): the small-graph pass below
+// has already united everything.
 __global__ void k_union_edges(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt, const Cnt n_edges,
-                              int32_t *__restrict__ parent, const int32_t *__restrict__ run_id) {
+                              int32_t *__restrict__ parent, const int32_t *__restrict__ run_id,
+                              const unsigned long long *__restrict__ done) {
+    if (done && *done) return;
     const long long E = n_edges.get();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
@@ -378,6 +383,86 @@ __global__ void k_union_edges(const int32_t *__restrict__ e_src, const int32_t *
             uf_union(parent, s, t);
         }
     }
+}
+
+// ---- small graphs (the regime Amira lives in: a few 10^4 nodes) ---------------------------------------------
+// A union is a chain of dependent loads, ~log n rounds of them while all edges hook at once; at L2 latency that is
+// ~80 us for a 30 000-node graph, a quarter of the whole build.  When the runs fit the shared memory of ONE CTA
+// the same unions run at shared-memory latency: the run-leaving edges are first collected into a compact list
+// (all SMs), then one CTA unites them in shared memory and writes every run's root back.
+constexpr int UF_SMALL_RUNS = 48 * 1024;   // runs (4 bytes each) one CTA holds
+constexpr int UF_SMALL_THREADS = 1024;
+
+__global__ void k_collect_run_edges(const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_tgt, const Cnt n_edges,
+                                    const Cnt n_nodes, const int32_t *__restrict__ run_id, unsigned long long *__restrict__ list,
+                                    unsigned long long *__restrict__ counter) {
+    const long long E = n_edges.get(), N = n_nodes.get();
+    if (N == 0 || run_id[N - 1] >= UF_SMALL_RUNS) return;  // too many runs: k_union_edges does the work
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; e0 < E; e0 += stride) {
+        const long long e = e0 + lane;
+        int a = 0, b = 0;
+        if (e < E) {
+            const int s = e_src[e], t = e_tgt[e];
+            if (s < t && t - s != 1) {
+                a = run_id[s];
+                b = run_id[t];
+            }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, a != b);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (a != b) list[base + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned int)a << 32) | (unsigned int)b;
+    }
+}
+
+__device__ __forceinline__ int uf_find_shared(int32_t *parent, int x) {
+    while (true) {
+        const int p = ((volatile int32_t *)parent)[x];
+        if (p == x) return x;
+        const int gp = ((volatile int32_t *)parent)[p];
+        if (gp == p) return p;
+        parent[x] = gp;
+        x = gp;
+    }
+}
+
+__global__ void __launch_bounds__(UF_SMALL_THREADS, 1)
+k_union_small(const unsigned long long *__restrict__ list, const unsigned long long *__restrict__ counter, const Cnt n_nodes,
+              const int32_t *__restrict__ run_id, int32_t *__restrict__ parent, unsigned long long *__restrict__ done) {
+    extern __shared__ int32_t s_parent[];
+    const long long N = n_nodes.get();
+    const int n_runs = N ? run_id[N - 1] + 1 : 0;
+    if (n_runs > UF_SMALL_RUNS) return;  // done stays 0
+    for (int i = threadIdx.x; i < n_runs; i += UF_SMALL_THREADS) s_parent[i] = i;
+    __syncthreads();
+    const long long n = (long long)*counter;
+    for (long long i = threadIdx.x; i < n; i += UF_SMALL_THREADS) {
+        const unsigned long long pr = list[i];
+        int ra = uf_find_shared(s_parent, (int)(pr >> 32)), rb = uf_find_shared(s_parent, (int)(pr & 0xFFFFFFFFull));
+        while (ra != rb) {
+            const unsigned int pa = uf_prio(ra), pb = uf_prio(rb);
+            if (pa < pb || (pa == pb && ra < rb)) {
+                const int t = ra;
+                ra = rb;
+                rb = t;
+            }
+            const int old = atomicCAS(&s_parent[ra], ra, rb);
+            if (old == ra) break;
+            ra = uf_find_shared(s_parent, old);
+            rb = uf_find_shared(s_parent, rb);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_runs; i += UF_SMALL_THREADS) {
+        int r = i;
+        for (int p = s_parent[r]; p != r; p = s_parent[r]) r = p;
+        parent[i] = r;
+    }
+    if (threadIdx.x == 0) *done = 1ull;
 }
 
 // runs of consecutive linked nodes: run_id = (number of run starts up to and including the node) - 1

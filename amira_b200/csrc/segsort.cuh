@@ -152,7 +152,20 @@ __global__ void __launch_bounds__(256) k_segsort_main(const SegJob J, const SegW
             sa = J.a_start ? (long long)J.a_start[s] : o;
         }
         unsigned int d = 0;
-        if (n >= 1 && n <= 8) {
+        if (n >= 1 && n <= 2) {
+            // most adjacency lists: one or two edges
+            const uint32_t *src = J.a + sa;
+            uint32_t *dst = dst_base + o;
+            uint32_t x = src[0], y = n == 2 ? src[1] : SEG_PAD;
+            ce(x, y);
+            if (n == 2) {
+                dst[0] = x;
+                dst[1] = y;
+                d = x == y;
+            } else if (dst != src) {
+                dst[0] = x;
+            }
+        } else if (n >= 3 && n <= 8) {
             uint32_t v[8];
             const uint32_t *src = J.a + sa;
             uint32_t *dst = dst_base + o;
