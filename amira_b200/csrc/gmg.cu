@@ -98,6 +98,9 @@ struct amira_gmg {
     DevBuf adj_off, adj_edges, adj_cursor, adj_tmp, reads_tmp;
     // scratch
     DevBuf dups, seg_work[2], scan_state[2], keep_n, keep_e, comp_max, scratch_off;
+    // tile states of all the scans of one build: cleared by ONE memset when the build is enqueued, handed out in pieces
+    DevBuf scan_pool;
+    size_t scan_pool_used = 0, scan_pool_ready = 0;
     DevBuf d_status, d_sizes;
     int *h_status = nullptr;       // pinned: [0] early copy, [ST_COUNT] final copy
     long long *h_sizes = nullptr;  // pinned: [0] early copy, [SZ_COUNT] final copy
@@ -201,12 +204,21 @@ inline int64_t scan_tiles(int64_t n_max) { return (n_max + 1 + SCAN_TILE - 1) / 
 // exclusive scan over items 0..n (n on the device or immediate, at most n_max) on the current stream
 template <typename L, typename S>
 int run_scan(amira_gmg *h, L load, S store, const long long *n_ptr, long long n_mul, long long n_imm, int64_t n_max) {
-    DevBuf &ws = h->scan_state[h->cur == h->stream2 ? 1 : 0];
     const int64_t tiles = scan_tiles(n_max);
-    AMIRA_TRY(ws.reserve(sizeof(unsigned long long) * (size_t)tiles));  // reserved by reserve_graph; grows otherwise
-    AMIRA_CUDA(cudaMemsetAsync(ws.p, 0, sizeof(unsigned long long) * (size_t)tiles, h->cur));
-    h->lib_launches++;
-    k_exscan<<<(unsigned int)(tiles - 1), SCAN_THREADS, 0, h->cur>>>(load, store, n_ptr, n_mul, n_imm, ws.as<unsigned long long>());
+    const size_t bytes = sizeof(unsigned long long) * (size_t)tiles;
+    unsigned long long *state;
+    if (h->scan_pool_used + bytes <= h->scan_pool_ready) {
+        // inside a build: a piece of the pool the build cleared when it was enqueued
+        state = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->scan_pool.p) + h->scan_pool_used);
+        h->scan_pool_used += bytes;
+    } else {
+        DevBuf &ws = h->scan_state[h->cur == h->stream2 ? 1 : 0];
+        AMIRA_TRY(ws.reserve(bytes));  // reserved by reserve_graph; grows otherwise
+        AMIRA_CUDA(cudaMemsetAsync(ws.p, 0, bytes, h->cur));
+        h->lib_launches++;
+        state = ws.as<unsigned long long>();
+    }
+    k_exscan<<<(unsigned int)(tiles - 1), SCAN_THREADS, 0, h->cur>>>(load, store, n_ptr, n_mul, n_imm, state);
     h->launches++;
     AMIRA_CUDA(cudaGetLastError());
     return AMIRA_OK;
@@ -438,6 +450,18 @@ int enqueue_insert(amira_gmg *h) {
     AMIRA_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int) * ST_COUNT, st));
     AMIRA_CUDA(cudaMemsetAsync(h->d_sizes.p, 0, sizeof(long long) * SZ_COUNT, st));
     h->lib_launches += 2;
+    h->scan_pool_used = h->scan_pool_ready = 0;
+    if (h->world == 1) {
+        // the seven scans of a one-GPU build (window offsets, first-seen ranks, runs, degrees, component firsts,
+        // read offsets + slack) share one cleared pool
+        const int64_t n_words = (G + 31) / 32;
+        const size_t need = sizeof(unsigned long long) * (size_t)(scan_tiles(R) + scan_tiles(n_words) + 3 * scan_tiles(h->cap_nodes) +
+                                                                  scan_tiles(2 * h->cap_nodes + 1) + 8);
+        AMIRA_TRY(h->scan_pool.reserve(need));
+        AMIRA_CUDA(cudaMemsetAsync(h->scan_pool.p, 0, need, st));
+        h->lib_launches++;
+        h->scan_pool_ready = need;
+    }
     {
         Phase ph(h, AMIRA_PH_WINDOWS);
         LAUNCH(h, k_read_windows, grid_for(R + 1, 256), 256, h->off, R, k, G, h->win_off.as<int64_t>(),
@@ -1445,7 +1469,7 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->reads_off, &h->reads, &h->node_key2, &h->node_cov2, &h->node_dir2, &h->node_comp2,
                       &h->reads_off2, &h->reads2, &h->parent, &h->link, &h->run_id, &h->run_pairs, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
                       &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
-                      &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->inc_rec, &h->unit_lo, &h->bucket_cursor, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->dups,
+                      &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->inc_rec, &h->unit_lo, &h->bucket_cursor, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->scan_pool, &h->dups,
                       &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,
                       &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rkey2, &h->x_rmeta2,
                       &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_sortk, &h->x_sortk2, &h->x_sorti,

@@ -53,8 +53,8 @@ enum {
     AMIRA_PH_WINDOWS = 1,    /* per-read window counts + scan */
     AMIRA_PH_INSERT = 2,     /* k_insert_windows: enumerate, canonicalise, hash, node + edge tables */
     AMIRA_PH_ORDER = 3,      /* first-seen ranks of nodes and edges (bitmap + prefix popcount) */
-    AMIRA_PH_REMAP = 4,      /* per-window slot -> node index */
-    AMIRA_PH_INCIDENCE = 5,  /* node -> reads CSR */
+    AMIRA_PH_REMAP = 4,      /* node -> reads offsets, units, partition pass (per-window slot -> node index + records dealt into buckets) */
+    AMIRA_PH_INCIDENCE = 5,  /* node -> reads CSR: one CTA per unit sorts its lists in shared memory */
     AMIRA_PH_ADJACENCY = 6,  /* node -> forward/backward edge CSR */
     AMIRA_PH_COMPONENTS = 7, /* connected components */
     AMIRA_PH_FILTER = 8,     /* last filter / component removal */

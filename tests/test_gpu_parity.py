@@ -330,6 +330,28 @@ def test_gpu_repeated_genemers_and_heavy_nodes(dg):
         assert O.diff_arrays(dg.arrays(), ref.arrays()) == [], k
 
 
+def test_gpu_node_confined_to_a_narrow_read_range(dg):
+    """the unit kernel cuts a long read list into equal-width READ ranges; a gene-mer that only occurs on a narrow
+    range of reads overfills a few of them (beyond what the warp networks take) and goes through the any-size
+    in-place sort.  Also a second heavy node spread over all reads beside it, and duplicates inside the range."""
+    from oracle import c_oracle
+    from oracle import gmg_oracle as O
+    rng = np.random.default_rng(11)
+    R = 400_000
+    body = rng.integers(10, 60000, (R, 3)).astype(np.int32) * rng.choice(np.array([-1, 1], np.int32), (R, 3))
+    reads = [body[i].tolist() for i in range(R)]
+    for i in range(3000):                      # (1,2,3) on reads 0..2999 only; twice on every 5th of them
+        reads[i] = [1, 2, 3] + ([7, 1, 2, 3] if i % 5 == 0 else [])
+    for i in range(0, R, 40):                  # (4,5,6) on every 40th read
+        if i >= 3000:
+            reads[i] = [4, 5, 6]
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    ids = np.concatenate([np.asarray(r, np.int32) for r in reads])
+    ref = c_oracle.COracleGraph(ids, off, 3)
+    dg.build(ids, off, 3)
+    assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
+
+
 def test_gpu_key_width_boundary_values(dg):
     """ids at the edge of the remembered key width (|id| = 2^(b-1) - 2 fits, -(2^(b-1) - 1) and -2^(b-1) must not be
     packed with b bits): the handle first sees V = 14, then ids that only use the two values beyond"""
