@@ -12,7 +12,7 @@ OK = 0
 E_BLANK_GENE, E_BAD_STRAND, E_EMPTY_NAME, E_UNKNOWN_GENE, E_PALINDROME, E_EMPTY_GENEMER, E_MULTI_EDGE = 1, 2, 3, 4, 5, 6, 7
 E_ARG, E_STATE, E_CUDA, E_NOMEM, E_NCCL = 8, 9, 10, 11, 12
 PHASES = ("h2d", "windows", "insert", "order", "remap", "incidence", "adjacency", "components", "filter",
-          "exchange", "emit", "insert_kernel", "emit_nodes")
+          "exchange", "emit", "insert_kernel", "emit_nodes", "exchange_edges")
 
 EXPORTED = (
     "amira_last_error", "amira_version", "amira_vocab_encode", "amira_host_tuple_sha", "amira_host_edge_keys", "amira_gmg_create", "amira_gmg_destroy",

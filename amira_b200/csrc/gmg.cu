@@ -242,7 +242,8 @@ void reset_graph(amira_gmg *h) {
     h->pending = 0;
 }
 
-int sharded_merge(amira_gmg *h);
+int sharded_merge_nodes(amira_gmg *h);
+int sharded_merge_edges(amira_gmg *h);
 
 // segmented sort on the current stream: segment s < *n_seg_ptr * mul has off[s+1] - off[s] keys below `max_value`;
 // in place (a_start == nullptr, out_of_place == false: `a` sorted, `b` is scratch) or from a (segment starts
@@ -568,16 +569,13 @@ int enqueue_order(amira_gmg *h) {
 // ---- the passes after the node order is known -------------------------------------------------------
 // branch B (second stream): edges in first-seen order, union-find, adjacency, components
 // branch A (main stream):   per-read node lists + node -> reads scatter, segment sort
-int enqueue_tail(amira_gmg *h) {
+// branch B, on the current stream (the caller has switched to the second one)
+int enqueue_tail_side(amira_gmg *h) {
     const int64_t G = h->G, n_words = (G + 31) / 32;
-    cudaStream_t st = h->stream;
     const Cnt N = dcnt(h, SZ_NODES), E = dcnt(h, SZ_EDGES);
     unsigned int *bm_node = h->bitmaps.as<unsigned int>();
     unsigned int *bm_ea = bm_node + (n_words + 1), *bm_eb = bm_ea + (n_words + 1);
-    AMIRA_CUDA(cudaEventRecord(h->ev_fork, st));
-    AMIRA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     {
-        SideStream side(h);
         unsigned long long *deg = h->adj_off.as<unsigned long long>();
         bool counted = false;
         const int32_t *run_ids = nullptr;
@@ -639,6 +637,14 @@ int enqueue_tail(amira_gmg *h) {
         }
         AMIRA_CUDA(cudaEventRecord(h->ev_join, h->cur));
     }
+    return AMIRA_OK;
+}
+
+// branch A, on the main stream
+int enqueue_tail_main(amira_gmg *h) {
+    const int64_t G = h->G;
+    cudaStream_t st = h->stream;
+    const Cnt N = dcnt(h, SZ_NODES);
     {
         // node -> reads (incidence.cuh): coverage per node (counted by the insert kernel) -> offsets, units,
         // records dealt into buckets (the same pass writes the per-read node lists), one CTA per unit
@@ -685,17 +691,33 @@ int enqueue_tail(amira_gmg *h) {
         h->launches++;
         AMIRA_CUDA(cudaGetLastError());
     }
-    AMIRA_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return AMIRA_OK;
+}
+
+int enqueue_join(amira_gmg *h) {
+    AMIRA_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     AMIRA_TRY(enqueue_report(h, 1));
     h->pending = 2;
     h->pending_is_build = true;
     return AMIRA_OK;
 }
 
+int enqueue_tail(amira_gmg *h) {
+    AMIRA_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    AMIRA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    {
+        SideStream side(h);
+        AMIRA_TRY(enqueue_tail_side(h));
+    }
+    AMIRA_TRY(enqueue_tail_main(h));
+    return enqueue_join(h);
+}
+
+// (a negative count leaves the size alone)
 __global__ void k_set_sizes(long long *sizes, long long n_nodes, long long n_edges) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        sizes[SZ_NODES] = n_nodes;
-        sizes[SZ_EDGES] = n_edges;
+        if (n_nodes >= 0) sizes[SZ_NODES] = n_nodes;
+        if (n_edges >= 0) sizes[SZ_EDGES] = n_edges;
     }
 }
 
@@ -787,9 +809,20 @@ int do_build(amira_gmg *h) {
     h->W = h->h_sizes[SZ_W];
     h->n_short = h->h_sizes[SZ_SHORT];
     h->prev_G = h->G;
-    AMIRA_TRY(sharded_merge(h));  // sets n_nodes / n_edges (global), reserves the graph arrays
-    LAUNCH(h, k_set_sizes, 1, 32, h->d_sizes.as<long long>(), (long long)h->n_nodes, (long long)h->n_edges);
-    return enqueue_tail(h);
+    // nodes first (main stream); then the per-read passes start on the main stream while the edges are exchanged,
+    // merged and emitted on the second one
+    AMIRA_TRY(sharded_merge_nodes(h));
+    LAUNCH(h, k_set_sizes, 1, 32, h->d_sizes.as<long long>(), (long long)h->n_nodes, -1ll);
+    AMIRA_CUDA(cudaEventRecord(h->ev_fork, st));
+    AMIRA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    AMIRA_TRY(enqueue_tail_main(h));
+    {
+        SideStream side(h);
+        AMIRA_TRY(sharded_merge_edges(h));
+        LAUNCH(h, k_set_sizes, 1, 32, h->d_sizes.as<long long>(), -1ll, (long long)h->n_edges);
+        AMIRA_TRY(enqueue_tail_side(h));
+    }
+    return enqueue_join(h);
 }
 
 // lazy removal of duplicate incidences (a gene-mer twice on one read), when the build counted any
@@ -1018,11 +1051,11 @@ int exchange_counts(amira_gmg *h, std::vector<int64_t> &send_off, std::vector<in
     const int world = h->world, me = h->rank;
     unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
     unsigned long long *d_mat = d_cnt + 2 * MAX_WORLD;
-    AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_mat, sizeof(unsigned long long) * world, h->stream));
+    AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_mat, sizeof(unsigned long long) * world, h->cur));
     AMIRA_CUDA(cudaMemcpyAsync(h->h_cnt, d_mat, sizeof(unsigned long long) * world * world, cudaMemcpyDeviceToHost,
-                               h->stream));
-    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, h->stream));
-    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+                               h->cur));
+    AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, h->cur));
+    AMIRA_CUDA(cudaStreamSynchronize(h->cur));
     send_off.assign(world + 1, 0);
     recv_off.assign(world + 1, 0);
     for (int p = 0; p < world; ++p) {
@@ -1048,10 +1081,10 @@ int gather_counts(amira_gmg *h, std::vector<int64_t> &off) {
     const int world = h->world;
     unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
     unsigned long long *d_mat = d_cnt + 2 * MAX_WORLD;
-    AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_mat, sizeof(unsigned long long), h->stream));
-    AMIRA_CUDA(cudaMemcpyAsync(h->h_cnt, d_mat, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, h->stream));
-    AMIRA_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, h->stream));
-    AMIRA_CUDA(cudaStreamSynchronize(h->stream));
+    AMIRA_TRY(comm_allgather(h->comm, d_cnt, d_mat, sizeof(unsigned long long), h->cur));
+    AMIRA_CUDA(cudaMemcpyAsync(h->h_cnt, d_mat, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, h->cur));
+    AMIRA_CUDA(cudaMemcpyAsync(h->h_status, h->d_status.p, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, h->cur));
+    AMIRA_CUDA(cudaStreamSynchronize(h->cur));
     off.assign(world + 1, 0);
     for (int p = 0; p < world; ++p) off[p + 1] = off[p] + h->h_cnt[p];
     return AMIRA_OK;
@@ -1074,7 +1107,7 @@ int publish_to_all(amira_gmg *h, bool p2p, const void *mine, int64_t n_mine, siz
                    h->world, dst);
         return AMIRA_OK;
     }
-    return comm_allgatherv(h->comm, mine, n_mine, fallback_recv, g_off.data(), elem, h->stream);
+    return comm_allgatherv(h->comm, mine, n_mine, fallback_recv, g_off.data(), elem, h->cur);
 }
 
 // AMIRA_SHARD_TRACE=1: per-step device times of the merge on stderr (developer aid)
@@ -1087,12 +1120,12 @@ struct MergeTrace {
         if (!on) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
-        cudaEventRecord(e, h->stream);
+        cudaEventRecord(e, h->cur);
         marks.push_back({name, e});
     }
     ~MergeTrace() {
         if (!on) return;
-        cudaStreamSynchronize(h->stream);
+        cudaStreamSynchronize(h->cur);
         std::string line = "[merge rank " + std::to_string(h->rank) + "]";
         for (size_t i = 1; i < marks.size(); ++i) {
             float ms = 0;
@@ -1106,13 +1139,14 @@ struct MergeTrace {
     }
 };
 
-int sharded_merge(amira_gmg *h) {
+// node half, on the main stream: afterwards every local slot knows its global node index and the global node
+// arrays are final, so the per-read passes can start while the edges are still being exchanged
+int sharded_merge_nodes(amira_gmg *h) {
     Phase ph(h, AMIRA_PH_EXCHANGE);
     MergeTrace tr(h);
     const int world = h->world, k = h->k, me = h->rank;
-    cudaStream_t st = h->stream;
+    cudaStream_t st = h->cur;
     const int tgrid_n = std::min<int>(grid_for(h->ncap, 256), h->n_sm * 16);
-    const int tgrid_e = std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16);
     const long long call_base = h->first_call_global;
     AMIRA_TRY(h->x_cnt.reserve(sizeof(unsigned long long) * (2 * MAX_WORLD + (size_t)world * world + 8)));
     unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
@@ -1250,6 +1284,23 @@ int sharded_merge(amira_gmg *h) {
     }
 
     tr.mark("n_global");
+    h->n_nodes = Ng;
+    h->prev_nodes = Nl;
+    return AMIRA_OK;
+}
+
+// edge half, on the CURRENT stream (the second one: it runs beside the per-read passes of the main stream)
+int sharded_merge_edges(amira_gmg *h) {
+    Phase ph(h, AMIRA_PH_EXCHANGE_EDGES);
+    MergeTrace tr(h);
+    const int world = h->world, me = h->rank;
+    cudaStream_t st = h->cur;
+    const int tgrid_e = std::min<int>(grid_for(h->ecap, 256), h->n_sm * 16);
+    const long long call_base = h->first_call_global;
+    const int64_t Ng = h->n_nodes;
+    unsigned long long *d_cnt = h->x_cnt.as<unsigned long long>();
+    std::vector<int64_t> send_off, recv_off, g_off;
+    bool p2p = comm_p2p(h->comm);
     // ---- edges: one record per locally-unique undirected adjacency, keyed on global node indices
     AMIRA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * MAX_WORLD, st));
     EdgeDst edst;
@@ -1345,9 +1396,7 @@ int sharded_merge(amira_gmg *h) {
     h->sh_Eg = Eg;
     h->sh_gedge = g_edge;
     tr.mark("e_global");
-    h->n_nodes = Ng;
     h->n_edges = E_dir;
-    h->prev_nodes = Nl;
     h->prev_und_edges = El + 1;
     return AMIRA_OK;
 }

@@ -63,7 +63,8 @@ enum {
                               * as are ADJACENCY and COMPONENTS) */
     AMIRA_PH_INSERT_KERNEL = 11, /* k_insert_windows alone (inside AMIRA_PH_INSERT, which also clears the tables) */
     AMIRA_PH_EMIT_NODES = 12,    /* node arrays in first-seen order */
-    AMIRA_PH_COUNT = 13
+    AMIRA_PH_EXCHANGE_EDGES = 13, /* multi-GPU: edge half of the exchange (second stream, beside REMAP / INCIDENCE) */
+    AMIRA_PH_COUNT = 14
 };
 
 const char *amira_last_error(void);
