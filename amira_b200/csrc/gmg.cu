@@ -50,7 +50,7 @@ struct amira_gmg {
     DevBuf cub_temp;
     int n_sm = 148;
     int insert_ctas_per_sm = 1;
-    int force_layout = 0;        // test hook (amira_gmg_debug_layout): 1 = no 16-byte node slots, 2 = no 16-byte edge slots, 4 = no packed keys
+    int force_layout = 0;        // test hook (amira_gmg_debug_layout): 1 = no 16-byte node slots, 2 = no 16-byte edge slots, 4 = no packed keys, 8 = the 16384-bucket shape of the partition pass, 16 = units share buckets pairwise
     int id_bits = 0;             // bits a signed gene id takes in a packed key (from the largest |id| seen); 0 = unknown
     bool n16 = false, e16 = false;  // 16-byte node / edge slots in the current build
     NodeView nview;
@@ -415,14 +415,15 @@ int reserve_graph(amira_gmg *h, int64_t capN, int64_t capE) {
         // INC_NB_MAX of them share buckets (a unit then sweeps its whole bucket)
         UnitPlan &u = h->unit_plan;
         const int64_t n_max = h->G / INC_C + std::min<int64_t>(capN, h->world > 1 ? capN : std::max<int64_t>(h->G, 1)) / INC_S + 2;
-        u.g = 0;
-        while (((n_max + (1ll << u.g) - 1) >> u.g) > INC_NB_MAX) ++u.g;
+        u.nb_max = (n_max <= INC_NB_MAX && !(h->force_layout & 8)) ? INC_NB_MAX : INC_NB_BIG;
+        u.g = (h->force_layout & 16) ? 2 : 0;
+        while (((n_max + (1ll << u.g) - 1) >> u.g) > u.nb_max) ++u.g;
         u.n_buckets = (int)((n_max + (1ll << u.g) - 1) >> u.g);
         u.n_units = u.n_buckets << u.g;
         u.read_lo = (uint32_t)h->first_read_global;
         u.rscale = (uint32_t)(0xFFFFFFFFull / (unsigned long long)std::max<int64_t>(R, 1));
         AMIRA_TRY(h->unit_lo.reserve(sizeof(int) * ((size_t)u.n_units + 2)));
-        AMIRA_TRY(h->bucket_cursor.reserve(sizeof(unsigned int) * 2 * INC_NB_MAX));  // cursors, then region starts
+        AMIRA_TRY(h->bucket_cursor.reserve(sizeof(unsigned int) * 2 * INC_NB_BIG));  // cursors, then region starts
     }
     for (int i = 0; i < 2; ++i)  // either stream may sort either array (the filter rebuilds the adjacency on the main one)
         AMIRA_TRY(h->seg_work[i].reserve(sizeof(long long) * (size_t)(std::max<int64_t>(G, capE) / SEG_BITONIC_MAX + 64 + 2)));
@@ -657,11 +658,18 @@ int enqueue_tail_main(amira_gmg *h) {
             LAUNCH(h, k_unit_table, (int)std::min<int64_t>(grid_for(std::max<int64_t>(h->ncap, h->cap_nodes + 1), 256), (int64_t)h->n_sm * 16), 256,
                    h->nview, h->reads_off.as<int64_t>(), dsz(h, SZ_NODES), u, h->unit_lo.as<int>(), h->d_status.as<int>());
             unsigned int *bcur = h->bucket_cursor.as<unsigned int>();
-            LAUNCH(h, k_bucket_base, INC_NB_MAX / 256, 256, h->unit_lo.as<int>(), h->reads_off.as<int64_t>(), u, bcur + INC_NB_MAX, bcur);
-            const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PART_TILE - 1) / PART_TILE), (int64_t)h->n_sm * PART_CTAS_V);
-            k_partition<<<pgrid, PART_THREADS, PART_SMEM, st>>>(h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(),
-                                                        h->win_node.as<int32_t>(), (const long long *)h->d_sizes.p, bcur + INC_NB_MAX, u, bcur,
-                                                        h->inc_rec.as<uint2>());
+            LAUNCH(h, k_bucket_base, u.nb_max / 256, 256, h->unit_lo.as<int>(), h->reads_off.as<int64_t>(), u, bcur + INC_NB_BIG, bcur);
+            if (u.nb_max == INC_NB_MAX) {
+                const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PartSmall::TILE - 1) / PartSmall::TILE), (int64_t)h->n_sm * PartSmall::CTAS);
+                k_partition<PartSmall><<<pgrid, PartSmall::THREADS, PartSmall::SMEM, st>>>(
+                    h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(), h->win_node.as<int32_t>(),
+                    (const long long *)h->d_sizes.p, bcur + INC_NB_BIG, u, bcur, h->inc_rec.as<uint2>());
+            } else {
+                const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PartBig::TILE - 1) / PartBig::TILE), (int64_t)h->n_sm * PartBig::CTAS);
+                k_partition<PartBig><<<pgrid, PartBig::THREADS, PartBig::SMEM, st>>>(
+                    h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(), h->win_node.as<int32_t>(),
+                    (const long long *)h->d_sizes.p, bcur + INC_NB_BIG, u, bcur, h->inc_rec.as<uint2>());
+            }
             h->launches++;
             AMIRA_CUDA(cudaGetLastError());
         }
@@ -1477,7 +1485,8 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     h->n_sm = prop.multiProcessorCount;
     AMIRA_CUDA(cudaFuncSetAttribute(k_unit_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INC_SMEM));
     AMIRA_CUDA(cudaFuncSetAttribute(k_union_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int32_t) * UF_SMALL_RUNS)));
-    AMIRA_CUDA(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PART_SMEM));
+    AMIRA_CUDA(cudaFuncSetAttribute(k_partition<PartSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PartSmall::SMEM));
+    AMIRA_CUDA(cudaFuncSetAttribute(k_partition<PartBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PartBig::SMEM));
     int occ = 1;
     AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_insert_windows<5, true, true>), INS_THREADS, 0));
     h->insert_ctas_per_sm = std::max(1, occ);

@@ -36,24 +36,28 @@ constexpr int INC_S = 4096;                  // nodes per unit at most
 constexpr int INC_CAPV = 16384;              // list entries a unit sorts in shared memory
 constexpr int INC_BIG = 4096;                // a last list up to this long never overflows a unit
 constexpr int INC_C = INC_CAPV - INC_BIG;    // window cell of the unit function
-constexpr int INC_NB_MAX = 4096;             // buckets the partition pass deals into
+constexpr int INC_NB_MAX = 4096;             // buckets the partition pass deals into (its small-CTA form)
+constexpr int INC_NB_BIG = 16384;            // ... in its one-CTA-per-SM form, for inputs with more units than that
 constexpr int INC_SUB_MIN = 8;               // lists up to this long are one sub-bucket
 constexpr int INC_THREADS = 512;             // two CTAs per SM: one sorts while the other streams its records in
 constexpr int INC_BATCH = 8;                 // records a thread has in flight
 constexpr int INC_CUR_WORDS = (INC_S + INC_CAPV / 2) / 2 + 8;  // 16-bit cursors, two to a word
 constexpr size_t INC_SMEM = sizeof(uint32_t) * (INC_CAPV + 4) + sizeof(uint16_t) * (INC_S + 8) + (INC_S + 8) + sizeof(uint32_t) * INC_CUR_WORDS;
 
-#ifndef PART_THREADS_V
-#define PART_THREADS_V 256
-#define PART_CTAS_V 3
-#endif
-constexpr int PART_THREADS = PART_THREADS_V;   // small CTAs, three to an SM (more do not help: the pass is bound by L2 transactions), which leaves registers for the second stream
-constexpr int PART_ITEMS = 8;
-constexpr int PART_TILE = PART_THREADS * PART_ITEMS;
-constexpr int PART_TOUCH = PART_TILE < INC_NB_MAX ? PART_TILE : INC_NB_MAX;
-constexpr size_t PART_SMEM = 2 * sizeof(uint32_t) * INC_NB_MAX + 2 * sizeof(uint16_t) * PART_TOUCH;
+// The partition pass comes in two shapes.  Up to INC_NB_MAX units (~45M gene calls): small CTAs, three to an SM
+// (more do not help: the pass is bound by L2 transactions), which leaves registers for the second stream.  Beyond:
+// 16384 buckets, whose counters take the shared memory of a whole SM, one CTA of 1024 threads on it.
+template <int NB_, int THREADS_, int CTAS_>
+struct PartShape {
+    static constexpr int NB = NB_, THREADS = THREADS_, CTAS = CTAS_, ITEMS = 8, TILE = THREADS_ * 8;
+    static constexpr int TOUCH = TILE < NB_ ? TILE : NB_;
+    static constexpr size_t SMEM = 2 * sizeof(uint32_t) * NB_ + 2 * sizeof(uint16_t) * TOUCH;
+};
+using PartSmall = PartShape<INC_NB_MAX, 256, 3>;
+using PartBig = PartShape<INC_NB_BIG, 1024, 1>;
 
 struct UnitPlan {
+    int nb_max;        // INC_NB_MAX or INC_NB_BIG: which shape of the partition pass runs
     int g;             // bucket = unit >> g
     int n_units;       // entries of unit_lo minus one; a multiple of 1 << g
     int n_buckets;     // n_units >> g
@@ -90,7 +94,7 @@ __global__ void k_unit_table(const NodeView nv, const int64_t *__restrict__ read
 __global__ void k_bucket_base(const int *__restrict__ unit_lo, const int64_t *__restrict__ reads_off, const UnitPlan plan,
                               uint32_t *__restrict__ bucket_base, unsigned int *__restrict__ bucket_cursor) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < INC_NB_MAX) {
+    if (b < plan.nb_max) {
         bucket_base[b] = b < plan.n_buckets ? (uint32_t)reads_off[unit_lo[b << plan.g]] : 0u;
         bucket_cursor[b] = 0;
     }
@@ -101,19 +105,21 @@ __global__ void k_bucket_base(const int *__restrict__ unit_lo, const int64_t *__
 // touched bucket in the bucket's region (one global atomic each), store the records at run start + rank.
 // The slots and reads of the NEXT tile are loaded before the current one is ranked, so the streams never stop
 // while a tile waits for its gathers, its reservations and its barriers.
-__global__ void __launch_bounds__(PART_THREADS, PART_CTAS_V)
+template <class S>
+__global__ void __launch_bounds__(S::THREADS, S::CTAS)
 k_partition(const uint2 *__restrict__ info, const int32_t *__restrict__ win_slot, const int32_t *__restrict__ win_read,
             int32_t *__restrict__ win_node, const long long *__restrict__ sizes, const uint32_t *__restrict__ bucket_base,
             const UnitPlan plan, unsigned int *__restrict__ bucket_cursor, uint2 *__restrict__ rec) {
     extern __shared__ __align__(16) unsigned char p_smem[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(p_smem);  // windows of the tile per bucket (zero between tiles)
-    uint32_t *run0 = hist + INC_NB_MAX;                     // where the tile's run starts in the record array
-    uint16_t (*touched)[PART_TOUCH] = reinterpret_cast<uint16_t (*)[PART_TOUCH]>(run0 + INC_NB_MAX);  // buckets the tile touched (double-buffered by tile parity)
+    constexpr int PART_THREADS = S::THREADS, PART_ITEMS = S::ITEMS, PART_TILE = S::TILE, PART_TOUCH = S::TOUCH;
+    uint32_t *run0 = hist + S::NB;                          // where the tile's run starts in the record array
+    uint16_t (*touched)[PART_TOUCH] = reinterpret_cast<uint16_t (*)[PART_TOUCH]>(run0 + S::NB);  // buckets the tile touched (double-buffered by tile parity)
     __shared__ uint32_t n_touched[2];
     const long long W = sizes[SZ_W];
     const int g = plan.g;
     const int tid = threadIdx.x;
-    for (int b = tid; b < INC_NB_MAX; b += PART_THREADS) hist[b] = 0;
+    for (int b = tid; b < S::NB; b += PART_THREADS) hist[b] = 0;
     if (tid < 2) n_touched[tid] = 0;
     __syncthreads();
     const long long n_tiles = (W + PART_TILE - 1) / PART_TILE;
@@ -149,7 +155,7 @@ k_partition(const uint2 *__restrict__ info, const int32_t *__restrict__ win_slot
                 __stcs(win_node + w0 + j, (int32_t)node[i]);
                 const uint32_t r = atomicAdd(&hist[br[i]], 1u);
                 if (r == 0) touched[par][atomicAdd(&n_touched[par], 1u)] = (uint16_t)br[i];
-                br[i] |= r << 12;  // bucket | rank within (tile, bucket): tiles of at most 2^20 windows
+                br[i] |= r << 14;  // bucket (< 2^14) | rank within (tile, bucket)
             }
         }
         __syncthreads();
@@ -167,7 +173,7 @@ k_partition(const uint2 *__restrict__ info, const int32_t *__restrict__ win_slot
 #pragma unroll
         for (int i = 0; i < PART_ITEMS; ++i) {
             const int j = i * PART_THREADS + tid;
-            if (j < cnt) rec[(size_t)(run0[br[i] & 4095u] + (br[i] >> 12))] = make_uint2(node[i], rd[i]);
+            if (j < cnt) rec[(size_t)(run0[br[i] & 16383u] + (br[i] >> 14))] = make_uint2(node[i], rd[i]);
             slot[i] = slot_n[i];
             rd[i] = rd_n[i];
         }

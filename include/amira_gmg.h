@@ -186,7 +186,8 @@ int amira_gmg_comm_init(amira_gmg *h, const void *nccl_unique_id, int rank, int 
 
 /* Test hook: forbid table layouts the library would otherwise choose from the input, so that the
  * rarely taken ones are exercised at small sizes.  mask bits: 1 = no 16-byte node slots, 2 = no
- * 16-byte edge slots, 4 = no packed keys (gene-mers compared through the ids array). */
+ * 16-byte edge slots, 4 = no packed keys (gene-mers compared through the ids array), 8 = the 16384-bucket
+ * shape of the partition pass, 16 = units of the node -> reads transpose share buckets. */
 int amira_gmg_debug_layout(amira_gmg *h, int mask);
 
 /* Test hook: the segmented sort behind the node -> reads and node -> edges lists, on host arrays:

@@ -67,7 +67,7 @@ def test_gpu_matches_c_oracle_on_synthetic(dg, cfg_name, n_reads, k, with_pos):
     assert O.diff_arrays(dg.arrays(), ref.arrays()) == []
 
 
-@pytest.mark.parametrize("mask", [1, 2, 3, 5, 7])
+@pytest.mark.parametrize("mask", [1, 2, 3, 5, 7, 8, 16, 24])
 @pytest.mark.parametrize("cfg_name,n_reads,k", [("c3", 30000, 3), ("c5", 20000, 5), ("c4", 20000, 7)])
 def test_gpu_every_table_layout(dg, mask, cfg_name, n_reads, k):
     """32-byte node slots (packed and unpacked keys) and 32-byte edge slots give the same graph as the 16-byte ones"""
