@@ -224,6 +224,9 @@ int run_scan(amira_gmg *h, L load, S store, const long long *n_ptr, long long n_
     return AMIRA_OK;
 }
 
+// gene calls one GPU takes: positions inside the node -> reads transpose are 32-bit (shard the reads beyond that)
+constexpr int64_t MAX_CALLS = 0xFFFF0000ll;
+
 int bits_for64(int64_t n) {
     int b = 1;
     while (b < 62 && (1ll << b) < n) ++b;
@@ -871,7 +874,7 @@ int finish(amira_gmg *h, bool early) {
                     int64_t G = 0;
                     AMIRA_CUDA(cudaMemcpyAsync(&G, h->off + h->R, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
                     AMIRA_CUDA(cudaStreamSynchronize(h->stream));
-                    if (G < 0 || G >= (1ll << (P_BITS - 1))) {
+                    if (G < 0 || G >= MAX_CALLS) {
                         set_error("bad call count %lld", (long long)G);
                         h->built = false;
                         return h->last_status = AMIRA_E_ARG;
@@ -1621,7 +1624,7 @@ int amira_gmg_build(amira_gmg *h, const int32_t *signed_ids, const int64_t *read
         } else {
             G = read_off[R];
         }
-        if (G < 0 || G >= (1ll << (P_BITS - 1)) || (G > 0 && !signed_ids)) {
+        if (G < 0 || G >= MAX_CALLS || (G > 0 && !signed_ids)) {
             set_error("bad call count %lld", (long long)G);
             h->cache_off = nullptr;
             arg_status = AMIRA_E_ARG;
