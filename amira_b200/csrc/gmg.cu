@@ -662,9 +662,16 @@ int enqueue_tail_main(amira_gmg *h) {
                    h->nview, h->reads_off.as<int64_t>(), dsz(h, SZ_NODES), u, h->unit_lo.as<int>(), h->d_status.as<int>());
             unsigned int *bcur = h->bucket_cursor.as<unsigned int>();
             LAUNCH(h, k_bucket_base, u.nb_max / 256, 256, h->unit_lo.as<int>(), h->reads_off.as<int64_t>(), u, bcur + INC_NB_BIG, bcur);
-            if (u.nb_max == INC_NB_MAX) {
+            // low coverage (by the previous build on this handle): large tiles, see incidence.cuh
+            const bool wide = h->prev_nodes > 0 && h->prev_G < (int64_t)PART_WIDE_BELOW * h->prev_nodes;
+            if (u.nb_max == INC_NB_MAX && !wide) {
                 const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PartSmall::TILE - 1) / PartSmall::TILE), (int64_t)h->n_sm * PartSmall::CTAS);
                 k_partition<PartSmall><<<pgrid, PartSmall::THREADS, PartSmall::SMEM, st>>>(
+                    h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(), h->win_node.as<int32_t>(),
+                    (const long long *)h->d_sizes.p, bcur + INC_NB_BIG, u, bcur, h->inc_rec.as<uint2>());
+            } else if (u.nb_max == INC_NB_MAX) {
+                const int pgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (G + PartWide::TILE - 1) / PartWide::TILE), (int64_t)h->n_sm * PartWide::CTAS);
+                k_partition<PartWide><<<pgrid, PartWide::THREADS, PartWide::SMEM, st>>>(
                     h->slot_info.as<uint2>(), h->win_slot.as<int32_t>(), h->win_read.as<int32_t>(), h->win_node.as<int32_t>(),
                     (const long long *)h->d_sizes.p, bcur + INC_NB_BIG, u, bcur, h->inc_rec.as<uint2>());
             } else {
@@ -1489,6 +1496,7 @@ int amira_gmg_create(amira_gmg **out, int device, void *cuda_stream) {
     AMIRA_CUDA(cudaFuncSetAttribute(k_unit_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INC_SMEM));
     AMIRA_CUDA(cudaFuncSetAttribute(k_union_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int32_t) * UF_SMALL_RUNS)));
     AMIRA_CUDA(cudaFuncSetAttribute(k_partition<PartSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PartSmall::SMEM));
+    AMIRA_CUDA(cudaFuncSetAttribute(k_partition<PartWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PartWide::SMEM));
     AMIRA_CUDA(cudaFuncSetAttribute(k_partition<PartBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PartBig::SMEM));
     int occ = 1;
     AMIRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_insert_windows<5, true, true>), INS_THREADS, 0));

@@ -44,24 +44,25 @@ constexpr int INC_BATCH = 8;                 // records a thread has in flight
 constexpr int INC_CUR_WORDS = (INC_S + INC_CAPV / 2) / 2 + 8;  // 16-bit cursors, two to a word
 constexpr size_t INC_SMEM = sizeof(uint32_t) * (INC_CAPV + 4) + sizeof(uint16_t) * (INC_S + 8) + (INC_S + 8) + sizeof(uint32_t) * INC_CUR_WORDS;
 
-// The partition pass comes in two shapes, both one CTA per SM on tiles of 8192 windows: 4096 buckets (up to ~45M gene
-// calls; 512 threads with 16 windows each in registers) or 16384 buckets, whose counters take most of an SM's shared
-// memory (1024 threads with 8 windows each).  Large tiles because
-// the reservations of one bucket are atomics on ONE address and L2 serialises those (~50 ns each): on low-coverage
-// graphs, where a tile touches most buckets with a record or two each, they set the pace (C3: 0.34 ms with 2048-window
-// tiles, 0.20 ms with 8192; the high-coverage C5 shard does not care: 0.39 / 0.40 ms).
+// The partition pass comes in three shapes.  Up to INC_NB_MAX units (~45M gene calls): small CTAs, three to an SM,
+// on tiles of 2048 windows -- on high-coverage graphs the pass is bound by L2 transactions whatever its shape, and
+// small CTAs leave room for the second stream (C5 shard: 1.94 ms per build against 2.03 ms with one big CTA per SM);
+// or one CTA per SM on tiles of 8192 windows (512 threads x 16 windows in registers) for LOW-coverage graphs, where a
+// tile touches most buckets with a record or two each: the reservations of one bucket are atomics on ONE address, L2
+// serialises those (~50 ns each), and the tile size sets the pace (C3: 0.34 ms with 2048-window tiles, 0.20 ms with
+// 8192).  Beyond INC_NB_MAX units: 16384 buckets, whose counters take most of an SM's shared memory, 1024 threads.
 template <int NB_, int THREADS_, int CTAS_, int ITEMS_ = 8>
 struct PartShape {
     static constexpr int NB = NB_, THREADS = THREADS_, CTAS = CTAS_, ITEMS = ITEMS_, TILE = THREADS_ * ITEMS_;
+    // (capping the small shape at 64 registers, to leave the second stream more of the register file, was measured
+    // SLOWER: 2.03 ms per build against 1.94 ms at the 72 registers the compiler takes)
+    static constexpr int REG_CTAS = CTAS_;
     static constexpr int TOUCH = TILE < NB_ ? TILE : NB_;
     static constexpr size_t SMEM = 2 * sizeof(uint32_t) * NB_ + 2 * sizeof(uint16_t) * TOUCH;
 };
-#ifndef PART_SMALL_T
-#define PART_SMALL_T 512
-#define PART_SMALL_C 1
-#define PART_SMALL_I 16
-#endif
-using PartSmall = PartShape<INC_NB_MAX, PART_SMALL_T, PART_SMALL_C, PART_SMALL_I>;
+using PartSmall = PartShape<INC_NB_MAX, 256, 3, 8>;
+using PartWide = PartShape<INC_NB_MAX, 512, 1, 16>;
+constexpr int PART_WIDE_BELOW = 16;   // windows per node (of the previous build on the handle) below which PartWide runs
 using PartBig = PartShape<INC_NB_BIG, 1024, 1>;
 
 struct UnitPlan {
@@ -114,7 +115,7 @@ __global__ void k_bucket_base(const int *__restrict__ unit_lo, const int64_t *__
 // The slots and reads of the NEXT tile are loaded before the current one is ranked, so the streams never stop
 // while a tile waits for its gathers, its reservations and its barriers.
 template <class S>
-__global__ void __launch_bounds__(S::THREADS, S::CTAS)
+__global__ void __launch_bounds__(S::THREADS, S::REG_CTAS)
 k_partition(const uint2 *__restrict__ info, const int32_t *__restrict__ win_slot, const int32_t *__restrict__ win_read,
             int32_t *__restrict__ win_node, const long long *__restrict__ sizes, const uint32_t *__restrict__ bucket_base,
             const UnitPlan plan, unsigned int *__restrict__ bucket_cursor, uint2 *__restrict__ rec) {
@@ -168,26 +169,13 @@ k_partition(const uint2 *__restrict__ info, const int32_t *__restrict__ win_slot
         }
         __syncthreads();
         {
-            // one reservation per touched bucket; all of a thread's atomics are in flight before the first result is used
             const int nt = (int)n_touched[par];
-            constexpr int RPT = PART_TOUCH / PART_THREADS;
-            int tb[RPT];
-            uint32_t got[RPT], bb[RPT];
-#pragma unroll
-            for (int u = 0; u < RPT; ++u) {
-                const int q = tid + u * PART_THREADS;
-                tb[u] = q < nt ? (int)touched[par][q] : -1;
-                got[u] = bb[u] = 0;
-                if (tb[u] >= 0) {
-                    const uint32_t c = hist[tb[u]];
-                    hist[tb[u]] = 0;
-                    bb[u] = bucket_base[tb[u]];
-                    got[u] = atomicAdd(&bucket_cursor[tb[u]], c);
-                }
+            for (int q = tid; q < nt; q += PART_THREADS) {
+                const int b = touched[par][q];
+                const uint32_t c = hist[b];
+                hist[b] = 0;
+                run0[b] = bucket_base[b] + atomicAdd(&bucket_cursor[b], c);
             }
-#pragma unroll
-            for (int u = 0; u < RPT; ++u)
-                if (tb[u] >= 0) run0[tb[u]] = bb[u] + got[u];
             if (tid == 0) n_touched[par ^ 1] = 0;
         }
         __syncthreads();
