@@ -6,8 +6,6 @@
 #include <algorithm>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>  // multi-GPU merge only (ordering of the merged records)
-
 #include "post_kernels.cuh"
 #include "stats.cuh"
 #include "sharded.cuh"
@@ -47,7 +45,6 @@ struct amira_gmg {
     cudaEvent_t ev_input_free = nullptr;
     int64_t piece_end[H2D_PIECES] = {};  // call index where each piece ends; 0 pieces = input already resident
     int n_pieces = 0;
-    DevBuf cub_temp;
     int n_sm = 148;
     int insert_ctas_per_sm = 1;
     int force_layout = 0;        // test hook (amira_gmg_debug_layout): 1 = no 16-byte node slots, 2 = no 16-byte edge slots, 4 = no packed keys, 8 = the 16384-bucket shape of the partition pass, 16 = units share buckets pairwise
@@ -146,8 +143,8 @@ struct amira_gmg {
     int64_t sh_Eg = 0;               // merged undirected edge records of the current sharded build
     const EdgeSlot *sh_gedge = nullptr;
     BuildParams local_P;             // parameters of the last k_insert_windows launch (the local tables)
-    DevBuf x_cnt, x_skey, x_smeta, x_rkey, x_rmeta, x_rkey2, x_rmeta2, x_mkey, x_mmeta, x_gkey, x_gmeta, x_tab,
-        x_sortk, x_sortk2, x_sorti, x_sorti2, x_sedge, x_redge, x_medge, x_gedge, x_etab, x_fan, cov_local;
+    DevBuf x_cnt, x_skey, x_smeta, x_rkey, x_rmeta, x_rmeta2, x_mkey, x_mmeta, x_gkey, x_gmeta, x_tab,
+        x_bm, x_pref, x_sorti2, x_sedge, x_redge, x_medge, x_gedge, x_etab, x_fan, cov_local;
     long long *h_cnt = nullptr;  // pinned, world*world + 4
 };
 
@@ -175,16 +172,6 @@ struct Phase {
         (h)->launches++;                                               \
         AMIRA_CUDA(cudaGetLastError());                                \
     } while (0)
-
-template <typename F>
-int cub_call(amira_gmg *h, F f) {
-    size_t bytes = 0;
-    AMIRA_CUDA(f(nullptr, bytes));
-    AMIRA_TRY(h->cub_temp.reserve(bytes ? bytes : 1));
-    AMIRA_CUDA(f(h->cub_temp.p, bytes));
-    h->lib_launches++;
-    return AMIRA_OK;
-}
 
 // launches inside this scope go to the second stream
 struct SideStream {
@@ -1052,15 +1039,19 @@ int do_filter(amira_gmg *h, int mode, uint32_t thr_node, uint32_t thr_edge) {
 
 // ---- multi-GPU: merge the local tables of all ranks into the global node / edge arrays ----------
 // (see sharded.cuh for the scheme)
-int sort_by_ord(amira_gmg *h, long long n) {
-    // x_sortk / x_sorti -> x_sortk2 / x_sorti2; keys are a global call position plus two flag bits
+// perm[rank by first global call position] = record, for n merged records (sharded.cuh: bitmap + prefix popcount)
+template <class Pos>
+int rank_by_position(amira_gmg *h, const Pos pos, long long n, unsigned int *perm) {
     if (n <= 0) return AMIRA_OK;
-    const int bits = std::min(P_BITS + 3, bits_for64(h->calls_global + 1) + 2);
-    return cub_call(h, [&](void *t, size_t &b) {
-        return cub::DeviceRadixSort::SortPairs(t, b, h->x_sortk.as<unsigned long long>(),
-                                               h->x_sortk2.as<unsigned long long>(), h->x_sorti.as<unsigned int>(),
-                                               h->x_sorti2.as<unsigned int>(), n, 0, bits, h->cur);
-    });
+    const int64_t n_words = h->calls_global / 32 + 1;
+    AMIRA_TRY(h->x_bm.reserve(sizeof(unsigned int) * (size_t)(n_words + 1)));
+    AMIRA_TRY(h->x_pref.reserve(sizeof(int) * (size_t)(n_words + 2)));
+    AMIRA_CUDA(cudaMemsetAsync(h->x_bm.p, 0, sizeof(unsigned int) * (size_t)(n_words + 1), h->cur));
+    h->lib_launches++;
+    LAUNCH(h, k_mark_ord<Pos>, grid_for(n, 256), 256, pos, n, h->x_bm.as<unsigned int>());
+    AMIRA_TRY(run_scan(h, BmLoad{h->x_bm.as<unsigned int>()}, BmStore{h->x_pref.as<int>()}, nullptr, 1, n_words, n_words));
+    LAUNCH(h, k_rank_ord<Pos>, grid_for(n, 256), 256, pos, n, h->x_bm.as<unsigned int>(), h->x_pref.as<int>(), perm);
+    return AMIRA_OK;
 }
 
 // counts[world] on the device -> the world x world matrix on the host (h_cnt[src * world + dst]);
@@ -1229,11 +1220,6 @@ int sharded_merge_nodes(amira_gmg *h) {
     tr.mark("n_a2a");
 
     // ---- owner merge: records in first-position order into a table (sum of counts, earliest record)
-    const int64_t sort_cap = std::max<int64_t>(Nr, 1);
-    AMIRA_TRY(h->x_sortk.reserve(sizeof(unsigned long long) * sort_cap));
-    AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * sort_cap));
-    AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * sort_cap));
-    AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * sort_cap));
     int64_t mcap = std::min<int64_t>(2 * Nr + 1024, 0x7FFFFFF0ll);
     AMIRA_TRY(h->x_tab.reserve(sizeof(NodeSlot) * mcap));
     AMIRA_TRY(h->x_mkey.reserve(key_bytes * std::max<int64_t>(Nr, 1)));
@@ -1286,13 +1272,8 @@ int sharded_merge_nodes(amira_gmg *h) {
     AMIRA_TRY(h->cov_local.reserve(sizeof(uint32_t) * (Ng + 1)));
     AMIRA_CUDA(cudaMemsetAsync(h->cov_local.p, 0, sizeof(uint32_t) * (Ng + 1), st));
     if (Ng > 0) {
-        AMIRA_TRY(h->x_sortk.reserve(sizeof(unsigned long long) * Ng));
-        AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * Ng));
-        AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * Ng));
         AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * Ng));
-        LAUNCH(h, k_rec_ord_keys, grid_for(Ng, 256), 256, g_meta, (long long)Ng,
-               h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
-        AMIRA_TRY(sort_by_ord(h, Ng));
+        AMIRA_TRY(rank_by_position(h, NodePos{g_meta}, (long long)Ng, h->x_sorti2.as<unsigned int>()));
         LAUNCH(h, k_finalize_nodes, grid_for(Ng, 256), 256, h->x_sorti2.as<unsigned int>(), g_key, g_meta, k, (long long)Ng, h->node_key.as<int32_t>(), h->node_cov.as<uint32_t>(),
                h->node_dir.as<int8_t>(), h->link.as<uint8_t>());
         // local slots -> global node indices: probe the rank's own node table with every global gene-mer
@@ -1390,13 +1371,8 @@ int sharded_merge_edges(amira_gmg *h) {
     int64_t E_dir = 0;
     AMIRA_TRY(h->x_fan.reserve(sizeof(int) * (Eg + 2)));
     if (Eg > 0) {
-        AMIRA_TRY(h->x_sortk.reserve(sizeof(unsigned long long) * Eg));
-        AMIRA_TRY(h->x_sortk2.reserve(sizeof(unsigned long long) * Eg));
-        AMIRA_TRY(h->x_sorti.reserve(sizeof(unsigned int) * Eg));
         AMIRA_TRY(h->x_sorti2.reserve(sizeof(unsigned int) * Eg));
-        LAUNCH(h, k_edge_ord_keys, grid_for(Eg, 256), 256, g_edge, (long long)Eg,
-               h->x_sortk.as<unsigned long long>(), h->x_sorti.as<unsigned int>());
-        AMIRA_TRY(sort_by_ord(h, Eg));
+        AMIRA_TRY(rank_by_position(h, EdgePos{g_edge}, (long long)Eg, h->x_sorti2.as<unsigned int>()));
         AMIRA_TRY(run_scan(h, FanLoad{h->x_sorti2.as<unsigned int>(), g_edge}, FanStore{h->x_fan.as<int>()}, nullptr, 1, Eg, Eg));
         int e_dir32 = 0;
         AMIRA_CUDA(cudaMemcpyAsync(&e_dir32, h->x_fan.as<int>() + Eg, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1539,9 +1515,9 @@ void amira_gmg_destroy(amira_gmg *h) {
                       &h->reads_off2, &h->reads2, &h->parent, &h->link, &h->run_id, &h->run_pairs, &h->is_root, &h->e_src, &h->e_tgt, &h->e_sd, &h->e_td,
                       &h->e_cov, &h->e_src2, &h->e_tgt2, &h->e_sd2, &h->e_td2, &h->e_cov2, &h->adj_off, &h->adj_edges,
                       &h->adj_cursor, &h->adj_tmp, &h->reads_tmp, &h->slot_info, &h->inc_rec, &h->unit_lo, &h->bucket_cursor, &h->win_slot, &h->seg_work[0], &h->seg_work[1], &h->scan_state[0], &h->scan_state[1], &h->scan_pool, &h->dups,
-                      &h->cub_temp, &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,
-                      &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rkey2, &h->x_rmeta2,
-                      &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_sortk, &h->x_sortk2, &h->x_sorti,
+                      &h->keep_n, &h->keep_e, &h->comp_max, &h->scratch_off, &h->d_status, &h->d_sizes,
+                      &h->x_cnt, &h->x_skey, &h->x_smeta, &h->x_rkey, &h->x_rmeta, &h->x_rmeta2,
+                      &h->x_mkey, &h->x_mmeta, &h->x_gkey, &h->x_gmeta, &h->x_tab, &h->x_bm, &h->x_pref,
                       &h->x_sorti2, &h->x_sedge, &h->x_redge, &h->x_medge, &h->x_gedge, &h->x_etab, &h->x_fan,
                       &h->cov_local, &h->cc_min, &h->d_maxabs};
     for (DevBuf *b : bufs) b->release();

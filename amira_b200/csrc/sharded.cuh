@@ -109,23 +109,43 @@ __global__ void k_node_route(const NodeView nv, const int32_t *__restrict__ ids,
     }
 }
 
-__global__ void k_rec_ord_keys(const NodeRec *__restrict__ meta, long long n, unsigned long long *__restrict__ keys,
-                               unsigned int *__restrict__ idx) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        keys[i] = meta[i].ord;
-        idx[i] = (unsigned int)i;
-    }
+// ---- first-seen order of merged records without a sort ------------------------------------------------
+// Every merged node (edge) has a distinct first global call position: a bitmap over the global call range, a prefix
+// popcount, and the rank of a record is the number of set bits below its own -- the same device as on one GPU
+// (post_kernels.cuh), over calls_global bits.  perm[rank] = record.
+struct NodePos {
+    const NodeRec *meta;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return meta[i].ord >> 1; }
+};
+struct EdgePos {
+    const EdgeSlot *recs;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return recs[i].ord >> 2; }
+};
+
+template <class Pos>
+__global__ void k_mark_ord(const Pos pos, long long n, unsigned int *__restrict__ bm) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long p = pos(i);
+    atomicOr(&bm[p >> 5], 1u << (p & 31));
 }
 
-__global__ void k_gather_node_recs(const unsigned int *__restrict__ perm, const int32_t *__restrict__ in_key,
-                                   const NodeRec *__restrict__ in_meta, int k, long long n,
-                                   int32_t *__restrict__ out_key, NodeRec *__restrict__ out_meta) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+struct BmLoad {
+    const unsigned int *bm;
+    __device__ __forceinline__ unsigned long long operator()(long long i) const { return (unsigned long long)__popc(bm[i]); }
+};
+struct BmStore {
+    int *pref;
+    __device__ __forceinline__ void operator()(long long i, unsigned long long excl, unsigned long long) const { pref[i] = (int)excl; }
+};
+
+template <class Pos>
+__global__ void k_rank_ord(const Pos pos, long long n, const unsigned int *__restrict__ bm, const int *__restrict__ pref,
+                           unsigned int *__restrict__ perm) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const long long s = perm[i];
-    for (int j = 0; j < k; ++j) out_key[i * k + j] = in_key[s * k + j];
-    out_meta[i] = in_meta[s];
+    const unsigned long long p = pos(i);
+    perm[pref[p >> 5] + __popc(bm[p >> 5] & ((1u << (p & 31)) - 1u))] = (unsigned int)i;
 }
 
 // records (canonical keys, k ids each, in the order they arrived) -> table; the slot names one record of the
@@ -324,15 +344,6 @@ __global__ void k_pack_merged_edges(const EdgeSlot *__restrict__ tab, unsigned i
         if (e.key == EMPTY64) continue;
         e.cov += 1u;   // counts from 0xFFFFFFFF: the sum of the merged pair counts
         out[reserve_one(counter)] = e;
-    }
-}
-
-__global__ void k_edge_ord_keys(const EdgeSlot *__restrict__ recs, long long n, unsigned long long *__restrict__ keys,
-                                unsigned int *__restrict__ idx) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        keys[i] = recs[i].ord;
-        idx[i] = (unsigned int)i;
     }
 }
 
