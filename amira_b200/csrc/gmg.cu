@@ -134,7 +134,7 @@ struct amira_gmg {
     cudaEvent_t ev[AMIRA_PH_COUNT][2] = {};
     bool ev_used[AMIRA_PH_COUNT] = {};
     int64_t launches = 0;      // hand-written kernels launched
-    int64_t lib_launches = 0;  // memset / memcpy calls (and CUB sorts of the multi-GPU merge)
+    int64_t lib_launches = 0;  // memset / memcpy calls
 
     // multi-GPU (sharded.cuh): exchange scratch, local coverage per global node
     Comm *comm = nullptr;

@@ -5,24 +5,26 @@
 // whole build is a handful of data-parallel passes:
 //
 //   k_read_windows     per read: window count (construct_read.py:41-43), short-read flag, and the
-//                      read that owns each 1024-call tile boundary
-//   k_insert_windows   THE hot kernel.  One CTA per 1024-call tile: coalesced 128-bit staging of
-//                      the tile (+k halo) in shared memory, read boundaries by a block max-scan,
-//                      per-window canonicalisation against the reverse complement
-//                      (construct_gene_mer.py:4-39), hash, insert into the node table with
+//                      read that owns each 128-call chunk boundary
+//   k_insert_windows   THE hot kernel (this file).  One warp per 128-call chunk, no block barriers:
+//                      128-bit staging of the chunk (+k halo) in per-warp shared memory, read
+//                      boundaries by a warp max-scan, per-window canonicalisation against the reverse
+//                      complement (construct_gene_mer.py:4-39), hash, insert into the node table with
 //                      first-seen tracking (atomicCAS / atomicMin on one 64-bit word), coverage
 //                      RED.ADD, per-window outputs, then adjacent-pair edges from the slot numbers
-//                      staged in shared memory (construct_graph.py:246-324)
-//   k_mark_first / k_popcount / k_emit_nodes / k_emit_edges
-//                      first-seen order without a sort: a bitmap over call positions + a prefix
-//                      popcount gives every node / edge its rank in upstream's dict order
-//   k_remap_windows    slot -> node index for the per-read node lists (construct_graph.py:165-178)
-//   k_incidence_*      node -> unique ascending reads (construct_node.py:64-67) from a stable radix
-//                      sort of (node, read) by node
-//   k_cc_*             connected components with lock-free union-find, numbered in first-node
-//                      order (construct_graph.py:911-927)
-//   k_filter_*         coverage / component thresholds + order-preserving stream compaction
-//                      (construct_graph.py:496-540, 950-958)
+//                      staged in shared memory (construct_graph.py:246-324), two probes in flight per lane
+//   post_kernels.cuh   first-seen order without a sort (a bitmap over call positions + a prefix popcount
+//                      gives every node / edge its rank in upstream's dict order), node / edge arrays
+//                      written coalesced through an inverse map, adjacency, connected components over
+//                      runs of consecutive nodes with a lock-free union-find (construct_graph.py:911-927),
+//                      filters: thresholds + order-preserving stream compaction (:496-540, 950-958)
+//   incidence.cuh      per-read node lists (construct_graph.py:165-178) and node -> unique ascending reads
+//                      (construct_node.py:64-67): a partition pass into per-unit buckets + one CTA per
+//                      unit sorting its lists in shared memory
+//   segsort.cuh        segmented sorts (adjacency lists; read lists beyond one CTA's shared memory)
+//   scan.cuh           single-pass look-back scans with device-side element counts
+//   stats.cuh          the post-build scans of the callers
+//   sharded.cuh        the multi-GPU exchange and merge
 #pragma once
 
 #include "common.cuh"

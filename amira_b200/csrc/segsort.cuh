@@ -1,12 +1,14 @@
 // segsort.cuh -- ascending sort of every segment of a CSR value array.
 //
 // Two users in the GeneMerGraph build, both the second half of a counting-sort "transpose":
+//   node -> edges    forward / backward edge lists in edge creation order (construct_graph.py:287-298):
+//                    k_segsort_main over the 2N adjacency segments.
 //   node -> reads    Node.listOfReads is the ascending list of the reads that touch the node
-//                    (construct_node.py:64-67).  The insert kernel counts the windows per node and hands
-//                    every window its arrival rank; a scatter pass drops the window's read at
-//                    (segment start + rank); the segments are sorted here.  Equal neighbours after the
-//                    sort are windows of one read (counted per node, removed lazily -- they are rare).
-//   node -> edges    forward / backward edge lists in edge creation order (construct_graph.py:287-298).
+//                    (construct_node.py:64-67).  incidence.cuh sorts these lists in shared memory; a list too
+//                    long for that is placed in global memory and handed to the work-list kernels here
+//                    (k_segsort_warp, k_segsort_radix), and a whole unit that outgrows shared memory runs the
+//                    loop of k_segsort_main over its own segments.  Equal neighbours after the sort are
+//                    windows of one read (counted per node, removed lazily -- they are rare).
 //
 // Segment sizes span five orders of magnitude (coverage-1 error nodes .. nodes on every read), so:
 //   n <= 1          copy
