@@ -299,9 +299,11 @@ int plan_build(amira_gmg *h) {
     // unique counts, scaled by the call-count ratio, size the tables; a cold build uses G/4 slots.
     // Either way an overflow is detected on the device and the build is redone larger.
     int64_t ncap = std::max<int64_t>(4096, G / 4), ecap = std::max<int64_t>(4096, G / 4);
-    // Load factor: a warp waits for the longest probe sequence among its lanes, so the 16-byte node table
-    // runs at ~30 % load (measured on the C5 shard: insert kernel 0.91 ms at 50 %, 0.78 ms at 30 %).
-    // The edge table is insensitive and stays at 50 %, as do the 32-byte layouts.
+    // Load factor: a warp waits for the longest probe sequence among its lanes, so the 16-byte node table runs
+    // below 50 % load: 42 % (2.4 slots per expected node).  Measured on the C5 shard, whole build: 1.97 ms at 1.6
+    // (62 %), 1.94 at 2.0, 1.92 at 2.4, 1.94 at 2.8, 1.98 at 3.2, 2.14 at 4.0 -- the insert kernel likes a sparse
+    // table, every pass that scans the table and the L2 like a small one.  The edge table is insensitive and stays
+    // at 50 %, as do the 32-byte layouts.
     if (h->id_bits == 0 && G > 0) {
         // first build on this handle: measure the largest |id| (later builds learn it from the insert kernel)
         if (h->n_pieces) AMIRA_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[h->n_pieces - 1], 0));  // needs every id
@@ -320,7 +322,7 @@ int plan_build(amira_gmg *h) {
     const bool n16 = T <= KEY16_BITS && h->id_bits > 0 && h->id_bits < 32 && !(h->force_layout & 1);
     h->key_bits = (T <= 124 && h->id_bits > 0 && h->id_bits < 32 && !(h->force_layout & 4)) ? h->id_bits : 0;
     const bool e16 = G < (1ll << ORD32_P_BITS) && !(h->force_layout & 2);
-    double nslack = n16 ? 3.2 : 2.0, eslack = 2.0;
+    double nslack = n16 ? 2.4 : 2.0, eslack = 2.0;
     if (const char *e = getenv("AMIRA_NODE_SLACK")) nslack = atof(e);  // developer experiments
     if (const char *e = getenv("AMIRA_EDGE_SLACK")) eslack = atof(e);
     if (h->hint_nodes > 0) ncap = h->hint_nodes * 2 + 1024;
