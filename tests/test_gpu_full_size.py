@@ -1,5 +1,6 @@
-"""Full-size runs of the BASELINE.json workloads on the GPU, checked through size-independent properties
-(the oracle would take too long here; bit-exact parity at oracle-sized inputs is in test_gpu_parity.py)."""
+"""Full-size runs of the BASELINE.json workloads on the GPU: size-independent properties, and bit-exact parity
+against the C oracle through committed digests of its builds of the same inputs (the oracle itself would take too
+long here; live oracle runs at oracle-sized inputs are in test_gpu_parity.py)."""
 import numpy as np
 import pytest
 
@@ -94,4 +95,52 @@ def test_full_size_invariants(cfg_name, n_reads, k):
     assert np.array_equal(gone, removed[win_before])
     assert np.array_equal(b["node_cov"], cov_before[~removed])
     assert np.array_equal(np.flatnonzero(b["to_correct"]), np.unique(win_read[gone]))
+    dg.close()
+
+
+def _golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_digests.json")) as f:
+        return json.load(f)
+
+
+def test_full_size_c5_shard_bit_exact_against_oracle_digests():
+    """the whole C5 shard (1.25M reads, 32.4M gene-mers, k=5): every exported array, digested, against the digests of
+    the C oracle's build of the same input (tests/golden/bench_digests.json, scripts/make_bench_digests.py)"""
+    from amira_b200 import synth
+    from amira_b200.device_graph import DeviceGraph
+    from oracle import digests
+    from dataclasses import replace
+    gold = _golden()["c5_n1"]
+    cfg = replace(synth.CONFIGS["c5"], n_reads=gold["reads"])   # as scripts/make_bench_digests.py and bench.py do
+    ids, off = synth.generate(cfg, 0, gold["reads"])
+    dg = DeviceGraph(0)
+    for _ in range(2):                      # cold tables, then tables sized from the first build: same graph
+        dg.build(ids, off, gold["k"])
+        a = dg.arrays()
+        assert digests.diff_digests(digests.global_digest(a), gold["global"]) == []
+        assert digests.diff_digests(digests.rank_digest(a), gold["ranks"][0]) == []
+    dg.close()
+
+
+@pytest.mark.parametrize("k", [3, 5, 7])
+def test_full_size_c3_through_the_filters_bit_exact_against_oracle_digests(k):
+    """C3 (500k reads, 10 % bad calls): build, remove_low_coverage_components(5), filter_graph(3, 1) -- every stage
+    against the C oracle's digests"""
+    from amira_b200 import synth
+    from amira_b200.device_graph import DeviceGraph
+    from oracle import digests
+    gold = _golden()["c3_k%d" % k]
+    ids, off = synth.generate(synth.CONFIGS["c3"], 0, gold["reads"])
+    dg = DeviceGraph(0)
+    dg.build(ids, off, k)
+    stages = (("build", lambda: None), ("rlcc5", lambda: dg.remove_low_coverage_components(5)),
+              ("rlcc5_filter3_1", lambda: dg.filter_graph(3, 1)))
+    for stage, step in stages:
+        step()
+        a = dg.arrays()
+        want = gold["stages"][stage]
+        assert digests.diff_digests(digests.global_digest(a), want["global"]) == [], stage
+        assert digests.diff_digests(digests.rank_digest(a), want["rank"]) == [], stage
     dg.close()
