@@ -29,7 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = os.environ.get("AMIRA_NVCC_FLAGS", "").split()       # developer experiments (e.g. -DAMIRA_INS_ILP=1)
     out = os.environ.get("AMIRA_LIB_OUT", LIB)
     cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
-          [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart"]
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -168,7 +168,16 @@ class GeneMerGraph:
             return
         self._lazy = False
         h = self._require_device_state()
-        self._materialise(h.arrays(), self._vocab)
+        # 10^5..10^6 long-lived objects are created in one go: the cyclic collector would re-scan them generation by
+        # generation on the way (measured on C2: 1.3 s -> 0.8 s without it); nothing here can form garbage cycles
+        import gc
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            self._materialise(h.arrays(), self._vocab)
+        finally:
+            if was_enabled:
+                gc.enable()
 
     def _arrays(self, *fields):
         """current device arrays of this graph (no host objects involved)"""
