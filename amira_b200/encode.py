@@ -55,9 +55,9 @@ class Vocabulary:
         return H
 
 
-def collect_names(reads: dict) -> set:
-    """unique gene names of a read dict (strand stripped, spaces -> '_')"""
-    toks = set(chain.from_iterable(reads.values()))
+def collect_names(reads: dict, toks=None) -> set:
+    """unique gene names of a read dict (strand stripped, spaces -> '_'); toks: the flattened calls, if the caller has them"""
+    toks = set(chain.from_iterable(reads.values()) if toks is None else toks)
     names = set()
     for t in toks:
         if not isinstance(t, str) or t.replace(" ", "") == "" or t[0] not in "+-" or len(t) < 2:
@@ -66,33 +66,42 @@ def collect_names(reads: dict) -> set:
     return names
 
 
-def encode_reads(reads: dict, vocab: Vocabulary, positions: dict | None = None):
+def encode_reads(reads: dict, vocab: Vocabulary, positions: dict | None = None, toks=None):
     """-> ids int32[G], off int64[R+1], pos_start, pos_end (or None, None)
 
     Raises AssertionError with upstream's messages for blank tokens, bad strand characters and
     empty names (through the C ABI's status codes), KeyError if a read has no positions entry."""
-    lens = np.fromiter((len(v) for v in reads.values()), np.int64, len(reads))
+    lens = np.fromiter(map(len, reads.values()), np.int64, len(reads))
     off = np.zeros(len(reads) + 1, np.int64)
     np.cumsum(lens, out=off[1:])
     G = int(off[-1])
-    toks = list(chain.from_iterable(reads.values()))
-    try:
-        blob = "".join(toks).encode("utf-8")
-    except TypeError:
-        _bad_token(next(t for t in toks if not isinstance(t, str)))
-    tok_off = np.zeros(G + 1, np.int64)
-    np.cumsum(np.fromiter(map(len, toks), np.int64, G), out=tok_off[1:])
-    if len(blob) != int(tok_off[-1]):          # non-ASCII gene names: byte lengths differ from str lengths
-        enc = [t.encode("utf-8") for t in toks]
-        np.cumsum(np.fromiter(map(len, enc), np.int64, G), out=tok_off[1:])
-        blob = b"".join(enc)
+    if toks is None:
+        toks = list(chain.from_iterable(reads.values()))
     vblob, voff = vocab.blob()
     ids = np.empty(G, np.int32)
     bad = C.c_int64(-1)
     lib = _lib.load()
-    status = lib.amira_vocab_encode(blob, tok_off.ctypes.data_as(C.c_void_p), G, vblob,
-                                    voff.ctypes.data_as(C.c_void_p), len(vocab),
-                                    ids.ctypes.data_as(C.c_void_p), C.byref(bad))
+    status = None
+    try:
+        # one blob, newline-separated: the C side splits it (no per-token length pass in Python).  A token with a
+        # newline or a NUL in it (no gene name has one) takes the offset form below.
+        joined = "\n".join(toks)
+    except TypeError:
+        _bad_token(next(t for t in toks if not isinstance(t, str)))
+    if G and joined.count("\n") == G - 1 and "\0" not in joined:
+        status = lib.amira_vocab_encode(joined.encode("utf-8"), None, G, vblob, voff.ctypes.data_as(C.c_void_p), len(vocab),
+                                        ids.ctypes.data_as(C.c_void_p), C.byref(bad))
+    if status is None:
+        blob = "".join(toks).encode("utf-8")
+        tok_off = np.zeros(G + 1, np.int64)
+        np.cumsum(np.fromiter(map(len, toks), np.int64, G), out=tok_off[1:])
+        if len(blob) != int(tok_off[-1]):          # non-ASCII gene names: byte lengths differ from str lengths
+            enc = [t.encode("utf-8") for t in toks]
+            np.cumsum(np.fromiter(map(len, enc), np.int64, G), out=tok_off[1:])
+            blob = b"".join(enc)
+        status = lib.amira_vocab_encode(blob, tok_off.ctypes.data_as(C.c_void_p), G, vblob,
+                                        voff.ctypes.data_as(C.c_void_p), len(vocab),
+                                        ids.ctypes.data_as(C.c_void_p), C.byref(bad))
     _lib.check(status)
     ps = pe = None
     if positions:
@@ -132,8 +141,9 @@ class EncodedReads:
         self.reads = reads
         self.positions = positions if positions else None
         self.read_ids = list(reads)
-        self.vocab = Vocabulary(collect_names(reads))
-        self.ids, self.off, self.pos_start, self.pos_end = encode_reads(reads, self.vocab, self.positions)
+        toks = list(chain.from_iterable(reads.values()))
+        self.vocab = Vocabulary(collect_names(reads, toks))
+        self.ids, self.off, self.pos_start, self.pos_end = encode_reads(reads, self.vocab, self.positions, toks)
         self._device = None
 
     def __len__(self):

@@ -74,8 +74,9 @@ const char *amira_version(void);
  * split_gene_and_strand (construct_gene.py:48-67) and convert_genes (construct_read.py:5-8).
  * Tokens are concatenated UTF-8 with tok_off[n_tok+1] byte offsets; vocabulary names likewise, in
  * SHA-rank order (names already have spaces replaced by '_').  Spaces in a token's name are mapped
- * to '_' before the lookup.  On error returns the code above and writes the index of the offending
- * token to *bad_token (if non-NULL). */
+ * to '_' before the lookup.  tok_off may be NULL: the tokens are then separated by '\n' in a NUL-terminated
+ * blob that must hold exactly n_tok of them.  On error returns the code above and writes the index of the
+ * offending token to *bad_token (if non-NULL). */
 int amira_vocab_encode(const char *tokens_utf8, const int64_t *tok_off, int64_t n_tok,
                        const char *vocab_utf8, const int64_t *vocab_off, int32_t n_vocab,
                        int32_t *out_signed_ids, int64_t *bad_token);
